@@ -1,0 +1,159 @@
+/* libi8ie_sm100.so — C ABI of the B200 (sm_100a) backend for the i8ie INT8 hot path.
+ *
+ * This is the drop-in boundary: it replaces the reference's L0+L1 for the path
+ * (Intel MKL CBLAS + the OpenMP loops around it, /root/reference include/layer.h:3)
+ * underneath the unchanged `i8ie` Python surface. The only C ABI the reference
+ * itself crosses on this path is
+ *     cblas_gemm_s8u8s32(RowMajor, NoTrans, Trans, RowOffset, m, n, k, 1, A_u8, k, 0,
+ *                        B_s8, k, 0, 0, C_s32, n, oc)          conv2d.cc:131-133
+ *                                                              fully_connected.cc:39-41
+ * with caller-owned buffers and no error return; every entry point below cites
+ * the reference code it replaces (file:line in /root/reference).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, scalars. No C++/torch types, no exceptions.
+ *  - every pointer is a DEVICE pointer unless the name ends in _host.
+ *  - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it.
+ *  - return 0 on success, a negative I8IE_E* code otherwise; i8ie_last_error()
+ *    returns a thread-local message for the last failure.
+ *  - the caller owns every buffer; plan objects own only their own descriptors /
+ *    packed-weight copies and are released with the matching *_destroy.
+ *  - activations (u8) are NHWC with a channel pitch `cp` that is a multiple of 16
+ *    bytes (pad lanes carry the tensor's zero_point); 2-D activations are
+ *    row-major with a row pitch that is a multiple of 16 bytes. fp32 tensors are
+ *    dense NCHW as in the reference (conv2d.cc:64-67).
+ *  - arithmetic contract (bit-exact vs the reference): SURVEY.md Appendix A.
+ */
+#ifndef I8IE_SM100_H
+#define I8IE_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define I8IE_API __attribute__((visibility("default")))
+#else
+#define I8IE_API
+#endif
+
+#define I8IE_OK 0
+#define I8IE_EINVAL (-1)   /* bad argument / unsupported shape */
+#define I8IE_ECUDA (-2)    /* CUDA runtime / driver error */
+#define I8IE_ENOTSM100 (-3) /* device is not compute capability 10.0 */
+
+#define I8IE_EPI_RELU 1     /* fuse relu<u8> (functional.cc:15-26): y = max(y, zp_out) */
+
+/* Version / diagnostics */
+I8IE_API const char* i8ie_last_error(void);
+I8IE_API const char* i8ie_version(void);
+I8IE_API int i8ie_device_check(void);          /* 0 iff the current device is sm_100 */
+/* Number of kernels this library has launched in this process (gpu_launches in bench.py). */
+I8IE_API int64_t i8ie_launch_count(void);
+
+/* ---- element-wise kernels (HBM-bound) ------------------------------------ */
+
+/* A1: quantize(Tensor<float>&, scale, zp), quantize_utils.cc:44-52 (unclamped, trunc):
+ *   q[i] = (u8)(int)(x[i] / scale + zp). Flat, dense. */
+I8IE_API int i8ie_quantize_f32_u8(const float* x, uint8_t* q, int64_t n, float scale, int zp, void* stream);
+
+/* Same arithmetic, fused with the NCHW(f32) -> NHWC(u8, pitch cp) re-layout the conv
+ * kernels consume; pad lanes [c, cp) are written with zp. */
+I8IE_API int i8ie_quantize_nchw_f32_nhwc_u8(const float* x, uint8_t* q, int n, int c, int h, int w, int cp,
+                                   float scale, int zp, void* stream);
+
+/* A5: dequantize(float*, u8*, size, scale, zp), quantize_utils.cc:38-42:
+ *   x[i] = (float)((int)q[i] - zp) * scale. Flat, dense. */
+I8IE_API int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, int zp, void* stream);
+/* Strided rows variant: q is [rows, pitch] (pitch >= cols), x dense [rows, cols]. */
+I8IE_API int i8ie_dequantize_rows_u8_f32(const uint8_t* q, float* x, int rows, int cols, int pitch,
+                                float scale, int zp, void* stream);
+
+/* A4: down_scale, quantize_utils.cc:27-36 (standalone requantise s32 -> u8):
+ *   d = ((float)acc*sa)*sb; r = d/sc + zp_c; y = r>=255 ? 255 : r<0 ? 0 : (u8)trunc(r). */
+I8IE_API int i8ie_downscale_s32_u8(const int32_t* acc, uint8_t* y, int64_t n, float sa, float sb, float sc,
+                          int zp_c, void* stream);
+
+/* A9 (reduction half): min/max of an fp32 buffer — what Calibrator::sample
+ * (calibrator.cc:6-23) + the sort in get_range (:25-27) yield for quantile 1 when
+ * every value is kept. out2 = {min, max} (device, 2 floats); workspace must hold
+ * i8ie_minmax_workspace_bytes() bytes and be zero-initialised once. */
+I8IE_API int64_t i8ie_minmax_workspace_bytes(void);
+I8IE_API int i8ie_minmax_f32(const float* x, int64_t n, float* out2, void* workspace, void* stream);
+/* A9 (scalar half): calibrator.cc:28-35 with (min,max) as input. Host function. */
+I8IE_API int i8ie_range_from_minmax_host(float mn, float mx, float* scale_host, uint8_t* zp_host);
+
+/* A10: relu<u8_t>, functional.cc:15-26: y = max(x, zp). Flat. */
+I8IE_API int i8ie_relu_u8(const uint8_t* x, uint8_t* y, int64_t n, int zp, void* stream);
+
+/* A11: max_pool2d<u8_t>, functional.cc:36-64 (no padding, floor): NHWC in (pitch cp)
+ * -> NHWC out (pitch cp), or, if out_nchw != 0, dense NCHW out (the flatten order
+ * x.reshape(-1, c*oh*ow) needs, tensor.h:106-133). */
+I8IE_API int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int c, int cp,
+                         int ksize, int stride, int out_nchw, void* stream);
+
+/* Layout glue for the NCHW-facing API (tensor.h:40-47 / pybind11.cc:14-15). */
+I8IE_API int i8ie_u8_nchw_to_nhwc(const uint8_t* x, uint8_t* y, int n, int c, int h, int w, int cp, int pad_value, void* stream);
+I8IE_API int i8ie_u8_nhwc_to_nchw(const uint8_t* x, uint8_t* y, int n, int c, int h, int w, int cp, void* stream);
+
+/* ---- weight preparation (once per model) ---------------------------------- */
+
+/* A8: quantize_weight, layer.cc:6-26. Host function on host buffers (runs once at
+ * convert()): shared min/max over weight U bias, scale=(max-min)/127, truncating
+ * unclamped casts. Returns the scale through *scale_host. */
+I8IE_API int i8ie_quantize_weight_host(const float* w_host, int64_t nw, const float* b_host, int64_t nb,
+                              int8_t* qw_host, int8_t* qb_host, float* scale_host);
+
+/* A2b / A3: zero-point + bias offsets, conv2d.cc:117-124 / fully_connected.cc:30-38.
+ * qw is the s8 weight in the REFERENCE's row order [n, K] (OIHW flattened), so the
+ * sequential fp32 accumulation of t is reproduced exactly:
+ *   t[j]  = sum_k (float)(in_zp * qw[j][k])            (fp32, k ascending)
+ *   conv: oc[j] = (int)((float)qb[j] / in_scale - t[j]);  bias_f[j] = 0
+ *   fc:   oc[j] = (int)(-t[j]);                          bias_f[j] = (float)qb[j] / in_scale
+ * oc and bias_f have n entries (device). */
+I8IE_API int i8ie_zp_offsets(const int8_t* qw, const int8_t* qb, int n, int k, int in_zp, float in_scale,
+                    int is_conv, int32_t* oc, float* bias_f, void* stream);
+
+/* Repack OIHW s8 weights into the kernels' K-major [kc_pad, kh, kw, cp] layout
+ * (zero in every pad lane / pad row). */
+I8IE_API int i8ie_pack_conv_weight(const int8_t* qw_oihw, int8_t* w_packed, int kc, int c, int kh, int kw,
+                          int kc_pad, int cp, void* stream);
+
+/* ---- the GEMM-shaped ops (tensor-core bound) -------------------------------- */
+
+typedef struct i8ie_conv_plan i8ie_conv_plan;
+
+/* Plan for Conv2d::forward_prop(Tensor<u8>&&), conv2d.cc:100-142, for one input
+ * geometry. w_packed is [kc_pad, kh, kw, cp] s8 (i8ie_pack_conv_weight) and must
+ * outlive the plan. x is NHWC u8 with pitch cp; y is NHWC u8 with pitch
+ * out_cp (multiple of 16, >= kc). Replaces im2col (conv2d.cc:34-49), the
+ * per-image cblas_gemm_s8u8s32 (:131-133), down_scale (:134-135) and transpose (:136).
+ * impl: 0 = auto, 1 = force the SIMT dp4a kernel, 2 = force tcgen05 (error if ineligible). */
+I8IE_API i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int kc, int kh, int kw,
+                                        int stride, int pad, int out_cp, const int8_t* w_packed,
+                                        int kc_pad, int impl);
+I8IE_API void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan);
+/* Which kernel the plan resolved to: 1 = SIMT dp4a, 2 = tcgen05. */
+I8IE_API int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan);
+/* y = requant(conv(x) + oc) [+relu]; sa=in.scale, sb=weight scale, sc=layer scale_,
+ * zp_in = in.zero_point (spatial padding value, conv2d.cc:129-130), zp_out = layer
+ * zero_point_. acc_out (optional, may be NULL) receives the s32 accumulators incl.
+ * oc as [n*oh*ow, kc] for parity tests. */
+I8IE_API int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int32_t* oc,
+                   float sa, float sb, float sc, int zp_in, int zp_out, int flags,
+                   int32_t* acc_out, void* stream);
+
+/* Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52:
+ *   acc = x[m,k] * w[n,k]^T + oc[n];  acc = (int)((float)acc + bias_f[n]);  y = requant(acc) [+relu]
+ * x pitch = ldx, w is [n_pad, ldw] s8 K-major (pad rows/lanes zero), y pitch = ldy.
+ * Dispatches on m only (small-m weight-streaming kernel vs tiled kernel). */
+I8IE_API int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+               int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
+               float sc, int zp_out, int flags, int32_t* acc_out, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I8IE_SM100_H */

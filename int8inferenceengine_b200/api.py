@@ -1,0 +1,140 @@
+"""The `i8ie` user API on the B200 backend — same names, signatures and behaviour as the
+reference's Python package (i8ie/__init__.py:1-32, tensor.py:4-37, layer.py:5-35,
+module.py:6-35), so existing scripts run unchanged with `import i8ie`.
+"""
+from __future__ import annotations
+
+from . import backend as _B
+from .workloads import INPUT_SCALE, INPUT_ZP
+
+__all__ = ["tensor", "argmax", "relu", "max_pool2d", "Linear", "Conv2d", "Tensor", "quantize",
+           "dequantize", "Module"]
+
+
+class Tensor:
+    """i8ie/tensor.py:4-37 — thin handle around a backend tensor (`.data`)."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def __repr__(self):
+        return ((self.numpy() - self.zero_point) * self.scale).__repr__()
+
+    def __eq__(self, obj):
+        # returns a RAW backend float tensor, as the reference does (tensor.py:11-12);
+        # the notebooks call `.sum()` on it.
+        return _B.tensor(self.numpy() == obj.numpy())
+
+    __hash__ = None
+
+    def reshape(self, *args):
+        return Tensor(self.data.reshape(list(args)))
+
+    def numpy(self):
+        return self.data.numpy()
+
+    def sum(self):
+        return self.numpy().sum()
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    @property
+    def scale(self):
+        return self.data.scale()
+
+    @property
+    def zero_point(self):
+        return self.data.zero_point()
+
+    @property
+    def dtype(self):
+        pass
+
+
+def tensor(ndarray):
+    return Tensor(_B.tensor(ndarray))
+
+
+def argmax(x, *args, **kwargs):
+    return tensor(x.numpy().argmax(*args, **kwargs))
+
+
+def relu(x):
+    return Tensor(_B.relu(x.data))
+
+
+def max_pool2d(x, kernel_size, stride):
+    return Tensor(_B.max_pool2d(x.data, kernel_size, stride))
+
+
+def quantize(x, scale, zero_point):
+    return Tensor(_B.quantize(x.data, scale, zero_point))
+
+
+def dequantize(x):
+    return Tensor(_B.dequantize(x.data))
+
+
+class Layer:
+    """i8ie/layer.py:5-19."""
+
+    def __call__(self, x):
+        return Tensor(self.layer(x.data))
+
+    def load_weight(self, weight):
+        self.layer.load_weight(weight)
+
+    def load_bias(self, bias):
+        self.layer.load_bias(bias)
+
+    def prepare(self):
+        self.layer.prepare()
+
+    def convert(self):
+        self.layer.convert()
+
+
+class Linear(Layer):
+    def __init__(self, in_channels, out_channels):
+        self.layer = _B.Linear(in_channels, out_channels)
+
+
+class Conv2d(Layer):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        self.layer = _B.Conv2d(in_channels, out_channels, kernel_size, stride, padding)
+
+
+class Module:
+    """i8ie/module.py:6-35."""
+
+    def __init__(self):
+        self.is_quant = False
+
+    def load(self, state_dict):
+        for key in state_dict:
+            name, attr = key.split(".")
+            if attr == "weight":
+                self.__dict__[name].load_weight(state_dict[key])
+            elif attr == "bias":
+                self.__dict__[name].load_bias(state_dict[key])
+
+    def __call__(self, x):
+        if self.is_quant:
+            x = Tensor(_B.quantize(x.data, INPUT_SCALE, INPUT_ZP))   # module.py:20 (hard-coded 0.025/127)
+        x = self.forward(x)
+        if self.is_quant:
+            x = Tensor(_B.dequantize(x.data))
+        return x
+
+    def prepare(self):
+        for _, val in self.__dict__.items():
+            if issubclass(type(val), Layer):
+                val.prepare()
+
+    def convert(self):
+        for _, val in self.__dict__.items():
+            if issubclass(type(val), Layer):
+                val.convert()
+        self.is_quant = True

@@ -1,0 +1,605 @@
+"""Backend object protocol of the B200 engine — the stand-in for the reference's pybind11
+module `_CXX_i8ie` (src/pybind11.cc:37-55, conv2d.cc:144-165, fully_connected.cc:54-72,
+functional.cc:66-82): functions tensor / quantize / dequantize / relu / max_pool2d, layer
+classes Linear / Conv2d, and tensor objects with numpy / zero_point / scale / sum /
+ref_count / reshape.
+
+Device memory is owned by torch tensors (glue); every INT8 op is a call into
+libi8ie_sm100.so through the C ABI (include/i8ie_sm100.h). There is no CPU fallback.
+
+Layouts. The API is logical NCHW (the reference's, conv2d.cc:64-67). Physically,
+  fp32 tensors          dense NCHW
+  u8 4-D activations    NHWC with channel pitch cp = round_up(C, 16)
+  u8 2-D activations    rows with pitch round_up(K, 16)  (NHWC with H = W = 1)
+  other u8 / s8         dense
+`numpy()` always returns the logical NCHW array (a D2H copy; the reference's is a
+zero-copy view of host memory, pybind11.cc:14-15 — mutation through the view is not
+carried over).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import I8ieError, check
+
+NUM_SAMPLES = 1000  # include/calibrator.h:4
+_F32_MAX_EXACT = 1 << 24
+
+
+def _r16(v):
+    return (int(v) + 15) // 16 * 16
+
+
+def _need_cuda():
+    if not torch.cuda.is_available():
+        raise I8ieError("no CUDA device visible: the i8ie B200 backend has no CPU fallback")
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _log(msg):
+    # the reference prints these through test_utils.h print() to stderr (layer.cc:30,38,42)
+    print(msg, file=sys.stderr)
+
+
+class _Storage:
+    """Stands in for the py::capsule that owns a Tensor's buffer (tensor.h:28,46,52,60)."""
+    __slots__ = ("t", "views")
+
+    def __init__(self, t):
+        self.t = t
+        self.views = 0
+
+
+class _TensorBase:
+    torch_dtype = None
+    np_dtype = None
+
+    def __init__(self, storage, shape, layout="dense", geom=None, scale=1.0, zp=0):
+        self._st = storage
+        storage.views += 1
+        self._shape = [int(s) for s in shape]
+        self._layout = layout          # 'dense' | 'nhwc'
+        self._geom = geom              # (n, c, h, w, cp) when layout == 'nhwc'
+        self._scale = np.float32(scale)  # tensor.h:153
+        self._zp = int(zp)               # tensor.h:154
+
+    def __del__(self):
+        try:
+            self._st.views -= 1
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # -- the methods src/pybind11.cc:12-30 binds --------------------------------------
+    def zero_point(self):
+        return self._zp
+
+    def scale(self):
+        return float(self._scale)
+
+    def ref_count(self):
+        return self._st.views
+
+    def numpy(self):
+        return self._dense_buf().view(self._shape).cpu().numpy()
+
+    def sum(self):
+        # pybind11.cc:18-25: sequential fp32 running sum
+        a = self.numpy().astype(np.float32).ravel()
+        return float(np.cumsum(a, dtype=np.float32)[-1]) if a.size else 0.0
+
+    def reshape(self, shape):
+        # Tensor::reshape, tensor.h:106-133 (one negative entry inferred; zeros rejected)
+        shape = [int(s) for s in shape]
+        size = int(np.prod(self._shape)) if self._shape else 1
+        midx, sz = -1, 1
+        for i, s in enumerate(shape):
+            if s < 0:
+                if midx != -1:
+                    raise RuntimeError("std::exception")
+                midx = i
+            elif s == 0:
+                raise RuntimeError("std::exception")
+            else:
+                sz *= s
+        if midx >= 0:
+            if size % sz != 0:
+                raise RuntimeError("std::exception")
+            shape[midx] = size // sz
+            sz *= shape[midx]
+        if sz != size:
+            raise RuntimeError("std::exception")
+        return self._view(shape)
+
+    # -- internals ---------------------------------------------------------------------
+    @property
+    def shape(self):
+        return tuple(self._shape)
+
+    @property
+    def buf(self):
+        return self._st.t
+
+    def _dense_buf(self):
+        """Flat torch tensor holding the logical (row-major NCHW) element order."""
+        return self._st.t
+
+    def _view(self, shape):
+        # tensor_view (tensor.h:94-104): shares the capsule, carries scale / zero_point
+        return type(self)(self._st, shape, "dense", None, self._scale, self._zp)
+
+
+class TensorF32(_TensorBase):
+    """Tensor<float> (`6TensorIfE`)."""
+    torch_dtype = torch.float32
+    np_dtype = np.float32
+
+
+class TensorS8(_TensorBase):
+    """Tensor<s8_t> (`6TensorIcE`) — quantised weights."""
+    torch_dtype = torch.int8
+    np_dtype = np.int8
+
+
+class TensorU8(_TensorBase):
+    """Tensor<u8_t> (`6TensorIhE`) — quantised activations, NHWC / padded rows on device."""
+    torch_dtype = torch.uint8
+    np_dtype = np.uint8
+
+    def _dense_buf(self):
+        if self._layout == "dense":
+            return self._st.t
+        n, c, h, w, cp = self._geom
+        if cp == c and h * w == 1:
+            return self._st.t
+        L = _need_cuda()
+        out = torch.empty(n * c * h * w, dtype=torch.uint8, device=self._st.t.device)
+        check(L.i8ie_u8_nhwc_to_nchw(self._st.t.data_ptr(), out.data_ptr(), n, c, h, w, cp, _stream()),
+              "u8_nhwc_to_nchw")
+        return out
+
+    def _view(self, shape):
+        if self._layout == "dense":
+            return TensorU8(self._st, shape, "dense", None, self._scale, self._zp)
+        n, c, h, w, cp = self._geom
+        if cp == c and h * w == 1:  # rows without padding: physical == logical
+            return TensorU8(self._st, shape, "dense", None, self._scale, self._zp)
+        # physical NHWC differs from the logical order: materialise the logical order once
+        return TensorU8(_Storage(self._dense_buf()), shape, "dense", None, self._scale, self._zp)
+
+    def _as_nhwc(self, n, c, h, w):
+        """(buffer, cp) of this tensor as NHWC with pitch round_up(c,16); converts if needed."""
+        cp = _r16(c)
+        if self._layout == "nhwc" and self._geom == (n, c, h, w, cp):
+            return self._st.t, cp
+        if self._layout == "dense" and h * w == 1 and cp == c:
+            return self._st.t, cp
+        L = _need_cuda()
+        src = self._dense_buf()
+        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=src.device)
+        check(L.i8ie_u8_nchw_to_nhwc(src.data_ptr(), out.data_ptr(), n, c, h, w, cp, self._zp, _stream()),
+              "u8_nchw_to_nhwc")
+        return out, cp
+
+
+def _new_u8_nhwc(buf, n, c, h, w, cp, scale, zp, two_d=False):
+    shape = [n, c] if two_d else [n, c, h, w]
+    return TensorU8(_Storage(buf), shape, "nhwc", (n, c, h, w, cp), scale, zp)
+
+
+# ---- module-level functions (src/pybind11.cc:38-48, functional.cc:66-82) -----------------
+
+def tensor(ndarray):
+    """_CXX_i8ie.tensor: py::array_t<float> force-casts anything array-like to f32 and copies
+    it in (tensor.h:40-47)."""
+    _need_cuda()
+    if isinstance(ndarray, torch.Tensor) and ndarray.device.type == "cpu":
+        # same force-cast; a pinned f32 tensor goes to the device without a staging copy
+        h = ndarray.detach().to(torch.float32).contiguous()
+        return TensorF32(_Storage(h.reshape(-1).to("cuda", non_blocking=True)), list(h.shape))
+    a = np.ascontiguousarray(np.asarray(ndarray), dtype=np.float32)
+    t = torch.from_numpy(a.reshape(-1).copy()).to("cuda", non_blocking=False)
+    return TensorF32(_Storage(t), list(a.shape))
+
+
+def tensor_from_torch(t):
+    """Extension (not in the reference): adopt a CUDA/CPU torch tensor without a host round trip."""
+    _need_cuda()
+    t = t.detach().to(device="cuda", dtype=torch.float32).contiguous()
+    return TensorF32(_Storage(t.reshape(-1)), list(t.shape))
+
+
+def quantize(x, scale, zero_point):
+    """quantize(Tensor<float>&, scale, zp) — quantize_utils.cc:44-52 (unclamped, truncating)."""
+    L = _need_cuda()
+    if not isinstance(x, TensorF32):
+        raise TypeError("quantize(): incompatible function arguments (expected a float tensor)")
+    zp = int(zero_point)
+    if not 0 <= zp <= 255:
+        raise TypeError("quantize(): zero_point must fit unsigned char")
+    scale = float(np.float32(scale))
+    src = x.buf
+    shp = x._shape
+    if len(shp) in (2, 4):
+        n, c = shp[0], shp[1]
+        h, w = (shp[2], shp[3]) if len(shp) == 4 else (1, 1)
+        cp = _r16(c)
+        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=src.device)
+        check(L.i8ie_quantize_nchw_f32_nhwc_u8(src.data_ptr(), out.data_ptr(), n, c, h, w, cp, scale, zp,
+                                               _stream()), "quantize_nchw_f32_nhwc_u8")
+        return _new_u8_nhwc(out, n, c, h, w, cp, scale, zp, two_d=(len(shp) == 2))
+    out = torch.empty(src.numel(), dtype=torch.uint8, device=src.device)
+    check(L.i8ie_quantize_f32_u8(src.data_ptr(), out.data_ptr(), src.numel(), scale, zp, _stream()),
+          "quantize_f32_u8")
+    return TensorU8(_Storage(out), shp, "dense", None, scale, zp)
+
+
+def dequantize(x):
+    """dequantize(Tensor<u8>&) — quantize_utils.cc:54-58 -> :38-42."""
+    L = _need_cuda()
+    if not isinstance(x, TensorU8):
+        raise TypeError("dequantize(): incompatible function arguments (expected a u8 tensor)")
+    numel = int(np.prod(x._shape)) if x._shape else 1
+    out = torch.empty(numel, dtype=torch.float32, device=x.buf.device)
+    if x._layout == "nhwc" and x._geom[2] * x._geom[3] == 1:
+        n, c, _, _, cp = x._geom
+        check(L.i8ie_dequantize_rows_u8_f32(x.buf.data_ptr(), out.data_ptr(), n, c, cp, x.scale(), x._zp,
+                                            _stream()), "dequantize_rows_u8_f32")
+    else:
+        src = x._dense_buf()
+        check(L.i8ie_dequantize_u8_f32(src.data_ptr(), out.data_ptr(), numel, x.scale(), x._zp, _stream()),
+              "dequantize_u8_f32")
+    return TensorF32(_Storage(out), x._shape)
+
+
+def relu(x):
+    """relu<T> — functional.cc:5-26. u8: max(x, zero_point) on device; fp32: torch glue."""
+    L = _need_cuda()
+    if isinstance(x, TensorU8):
+        out = torch.empty_like(x.buf)
+        check(L.i8ie_relu_u8(x.buf.data_ptr(), out.data_ptr(), x.buf.numel(), x._zp, _stream()), "relu_u8")
+        return TensorU8(_Storage(out), x._shape, x._layout, x._geom, x._scale, x._zp)
+    if isinstance(x, TensorF32):
+        return TensorF32(_Storage(torch.relu(x.buf)), x._shape)
+    raise TypeError("relu(): unsupported tensor type")
+
+
+def max_pool2d(x, kernel_size, strides):
+    """max_pool2d<T> — functional.cc:36-64 (no padding, floor output size)."""
+    L = _need_cuda()
+    k, s = int(kernel_size), int(strides)
+    if len(x._shape) != 4:
+        raise RuntimeError("max_pool2d expects a 4-d tensor")
+    n, c, h, w = x._shape
+    if k < 1 or s < 1 or h < k or w < k:
+        raise RuntimeError("max_pool2d: window larger than input")
+    oh, ow = (h - k) // s + 1, (w - k) // s + 1
+    if isinstance(x, TensorU8):
+        buf, cp = x._as_nhwc(n, c, h, w)
+        out = torch.empty(n * oh * ow * cp, dtype=torch.uint8, device=buf.device)
+        check(L.i8ie_maxpool_u8_nhwc(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, k, s, 0, _stream()),
+              "maxpool_u8_nhwc")
+        return _new_u8_nhwc(out, n, c, oh, ow, cp, x._scale, x._zp)
+    if isinstance(x, TensorF32):
+        y = torch.nn.functional.max_pool2d(x.buf.view(n, c, h, w), k, s)
+        return TensorF32(_Storage(y.contiguous().reshape(-1)), [n, c, oh, ow])
+    raise TypeError("max_pool2d(): unsupported tensor type")
+
+
+# ---- calibrator (include/calibrator.h, src/calibrator.cc) ---------------------------------
+
+class Calibrator:
+    """Activation-range collector. The reference keeps a 1000-slot sample with random
+    replacement from an unseeded mt19937 (calibrator.cc:6-23) and takes min/max of the sorted
+    slots (get_range(1), :24-37). Here the range is the true min/max of everything seen —
+    a warp-shuffle/block reduction on the device (i8ie_minmax_f32) — which is what the
+    reference computes whenever <=1000 values were seen; for exactly that regime the first
+    1000 values are also kept so the zero-filled-tail quirk is reproduced."""
+
+    def __init__(self):
+        self.out_cnt = 0
+        self.head = []          # first <=1000 samples, host copies
+        self.mn = None
+        self.mx = None
+        self._ws = None
+        self._out = None
+
+    def sample(self, t):
+        L = _need_cuda()
+        n = t.numel()
+        if n == 0:
+            return
+        if self.out_cnt < NUM_SAMPLES:
+            take = min(NUM_SAMPLES - self.out_cnt, n)
+            self.head.append(t.reshape(-1)[:take].cpu().numpy())
+        if self._ws is None:
+            self._ws = torch.zeros(int(L.i8ie_minmax_workspace_bytes()), dtype=torch.uint8, device=t.device)
+            self._out = torch.empty(2, dtype=torch.float32, device=t.device)
+        check(L.i8ie_minmax_f32(t.data_ptr(), n, self._out.data_ptr(), self._ws.data_ptr(), _stream()),
+              "minmax_f32")
+        mn, mx = (float(v) for v in self._out.cpu().numpy())
+        self.mn = mn if self.mn is None else min(self.mn, mn)
+        self.mx = mx if self.mx is None else max(self.mx, mx)
+        self.out_cnt += n
+
+    def get_range(self):
+        L = _lib.load()
+        if self.out_cnt == 0:
+            raise RuntimeError("convert() after prepare() needs at least one calibration forward pass")
+        if self.out_cnt <= NUM_SAMPLES:
+            buf = np.zeros(NUM_SAMPLES, np.float32)        # value-initialised slots (layer.cc:33)
+            head = np.concatenate(self.head)
+            buf[:head.size] = head
+            buf.sort()                                      # calibrator.cc:25
+            mn, mx = buf[0], buf[self.out_cnt - 1]          # :26-27 with quantile 1
+        else:
+            mn, mx = self.mn, self.mx
+        sc, zp = C.c_float(), C.c_uint8()
+        check(L.i8ie_range_from_minmax_host(float(mn), float(mx), C.byref(sc), C.byref(zp)))
+        return np.float32(sc.value), int(zp.value)
+
+
+# ---- layers (include/layer.h, src/layer.cc, conv2d.cc, fully_connected.cc) ----------------
+
+class _BaseLayer:
+    def __init__(self, weight_shape, out_channel):
+        _need_cuda()
+        # BaseLayer ctor allocates uninitialised weight/bias (layer.h:9-12)
+        self._w = np.zeros(weight_shape, np.float32)
+        self._b = np.zeros((out_channel,), np.float32)
+        self._w_dev = None
+        self._b_dev = None
+        self._cal = None
+        self._is_preparing = False
+        self._is_quantized = False
+        self._scale = np.float32(1.0)   # layer.h:46
+        self._zp = 0                    # layer.h:47
+        self._w_scale = None
+        self._qw_dev = None             # s8, reference row order [n, K]
+        self._qb_dev = None
+        self._w_packed = None           # s8, kernel layout
+        self._oc_cache = {}
+        self._plans = {}
+        self.fuse_relu = False          # extension: fold a following relu<u8> into the epilogue
+
+    def load_weight(self, w):
+        if self._w is None:
+            raise RuntimeError("std::exception")      # layer.h:16-18
+        self._w = np.ascontiguousarray(np.asarray(w), dtype=np.float32)
+        self._w_dev = None
+
+    def load_bias(self, b):
+        if self._w is None:
+            raise RuntimeError("std::exception")      # layer.h:22-24
+        self._b = np.ascontiguousarray(np.asarray(b), dtype=np.float32)
+        self._b_dev = None
+
+    def prepare(self):
+        if self._is_quantized:
+            _log("already quantized")                 # layer.cc:29-32
+            return
+        self._cal = Calibrator()
+        self._is_preparing = True
+
+    def set_qparams(self, scale, zero_point):
+        """Extension hook (not in the reference): inject a calibrated (scale, zero_point),
+        e.g. the ones a reference run produced, before convert(). The reference's own
+        calibrator is randomised beyond 1000 samples, so parity runs pin ranges this way."""
+        self._scale = np.float32(scale)
+        self._zp = int(zero_point)
+        self._cal = None
+        self._is_preparing = False
+        self._injected = True
+
+    def convert(self):
+        L = _need_cuda()
+        if self._is_quantized:
+            _log("already quantized")                 # layer.cc:37-40
+            return
+        if not self._is_preparing:
+            if not getattr(self, "_injected", False):
+                _log("No prepared, use default config")   # layer.cc:41-42
+        else:
+            self._scale, self._zp = self._cal.get_range()  # layer.cc:44
+            self._cal = None
+        qw = np.empty(self._w.shape, np.int8)
+        qb = np.empty(self._b.shape, np.int8)
+        sc = C.c_float()
+        check(L.i8ie_quantize_weight_host(self._w.ctypes.data, self._w.size, self._b.ctypes.data, self._b.size,
+                                          qw.ctypes.data, qb.ctypes.data, C.byref(sc)), "quantize_weight_host")
+        self._w_scale = np.float32(sc.value)
+        self._qw_dev = torch.from_numpy(qw.reshape(qw.shape[0], -1)).cuda()
+        self._qb_dev = torch.from_numpy(qb).cuda()
+        self._qw_shape = qw.shape
+        self._pack()
+        self._is_preparing = False
+        self._is_quantized = True
+        self._w = None          # layer.cc:52-53 frees the fp32 parameters
+        self._b = None
+        self._w_dev = None
+        self._b_dev = None
+
+    # extension accessors used by parity tests
+    def q_weight(self):
+        return TensorS8(_Storage(self._qw_dev.reshape(-1)), list(self._qw_shape), scale=self._w_scale)
+
+    def q_bias(self):
+        return TensorS8(_Storage(self._qb_dev), [self._qb_dev.numel()], scale=self._w_scale)
+
+    def _offsets(self, in_zp, in_scale, is_conv):
+        key = (int(in_zp), float(in_scale))
+        hit = self._oc_cache.get(key)
+        if hit is None:
+            L = _lib.load()
+            n, k = self._qw_dev.shape
+            oc = torch.empty(n, dtype=torch.int32, device="cuda")
+            bf = torch.empty(n, dtype=torch.float32, device="cuda")
+            check(L.i8ie_zp_offsets(self._qw_dev.data_ptr(), self._qb_dev.data_ptr(), n, k, int(in_zp),
+                                    float(in_scale), int(is_conv), oc.data_ptr(), bf.data_ptr(), _stream()),
+                  "zp_offsets")
+            hit = (oc, bf)
+            self._oc_cache[key] = hit
+        return hit
+
+    def _fp32_params(self):
+        if self._w_dev is None:
+            self._w_dev = torch.from_numpy(self._w).cuda()
+        if self._b_dev is None:
+            self._b_dev = torch.from_numpy(self._b).cuda()
+        return self._w_dev, self._b_dev
+
+    def __call__(self, x):
+        if isinstance(x, TensorF32):
+            if self._w is None:
+                raise RuntimeError("layer was converted: fp32 parameters are released (layer.cc:52-53)")
+            return self._forward_f32(x)
+        if isinstance(x, TensorU8):
+            if not self._is_quantized:
+                raise RuntimeError("layer is not converted: call prepare()/convert() before a u8 forward")
+            return self._forward_u8(x)
+        raise TypeError("__call__(): incompatible function arguments")
+
+
+class _tf32_off:
+    def __enter__(self):
+        self.a = torch.backends.cuda.matmul.allow_tf32
+        self.b = torch.backends.cudnn.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.a
+        torch.backends.cudnn.allow_tf32 = self.b
+
+
+class Linear(_BaseLayer):
+    """Linear — include/fully_connected.h, src/fully_connected.cc."""
+
+    def __init__(self, in_channel, out_channel):
+        super().__init__((int(out_channel), int(in_channel)), int(out_channel))
+
+    def _pack(self):
+        n, k = self._qw_dev.shape
+        self._ldw = _r16(k)
+        self._n_pad = _r16(n)
+        wp = torch.zeros(self._n_pad, self._ldw, dtype=torch.int8, device="cuda")
+        wp[:n, :k] = self._qw_dev
+        self._w_packed = wp
+
+    def _forward_f32(self, x):
+        # Linear::forward_prop(Tensor<float>&&), fully_connected.cc:5-21 — fp32 side is torch
+        # glue (TF32 off); it only feeds the calibrator.
+        w, b = self._fp32_params()
+        m = x._shape[0]
+        with _tf32_off():
+            y = torch.nn.functional.linear(x.buf.view(m, -1), w, b).contiguous()
+        if self._is_preparing:
+            self._cal.sample(y)                       # fully_connected.cc:17-19
+        return TensorF32(_Storage(y.reshape(-1)), [m, w.shape[0]])
+
+    def _forward_u8(self, x, acc_out=None, impl=0):
+        # Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52
+        L = _lib.load()
+        if len(x._shape) != 2:
+            raise RuntimeError("Linear expects a 2-d tensor")
+        m, k = x._shape
+        n, kw = self._qw_dev.shape
+        if k != kw:
+            raise RuntimeError(f"Linear: input has {k} features, weight expects {kw}")
+        buf, ldx = x._as_nhwc(m, k, 1, 1)
+        oc, bf = self._offsets(x._zp, x.scale(), False)
+        ldy = _r16(n)
+        out = torch.empty(m * ldy, dtype=torch.uint8, device=buf.device)
+        flags = 1 if self.fuse_relu else 0
+        check(L.i8ie_fc_u8(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
+                           out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
+                           float(self._w_scale), float(self._scale), self._zp, flags,
+                           acc_out.data_ptr() if acc_out is not None else None, impl, _stream()), "fc_u8")
+        return _new_u8_nhwc(out, m, n, 1, 1, ldy, self._scale, self._zp, two_d=True)
+
+
+class Conv2d(_BaseLayer):
+    """Conv2d — include/conv2d.h, src/conv2d.cc."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        if int(stride) == 0:
+            raise RuntimeError("std::exception")      # conv2d.h:12-14
+        super().__init__((int(out_channels), int(in_channels), int(kernel_size), int(kernel_size)),
+                         int(out_channels))
+        self._stride = int(stride)
+        self._pad = int(padding)
+
+    def _pack(self):
+        L = _lib.load()
+        kc, c, kh, kw = self._qw_shape
+        self._cp = _r16(c)
+        self._kc_pad = _r16(kc)
+        wp = torch.empty(self._kc_pad * kh * kw * self._cp, dtype=torch.int8, device="cuda")
+        check(L.i8ie_pack_conv_weight(self._qw_dev.data_ptr(), wp.data_ptr(), kc, c, kh, kw, self._kc_pad,
+                                      self._cp, _stream()), "pack_conv_weight")
+        self._w_packed = wp
+
+    def _forward_f32(self, x):
+        # Conv2d::forward_prop(Tensor<float>&&), conv2d.cc:63-98 — torch glue, TF32 off
+        w, b = self._fp32_params()
+        n, c, h, wd = x._shape
+        with _tf32_off():
+            y = torch.nn.functional.conv2d(x.buf.view(n, c, h, wd), w, b, stride=self._stride,
+                                           padding=self._pad).contiguous()
+        if self._is_preparing:
+            self._cal.sample(y)                       # conv2d.cc:94-96
+        return TensorF32(_Storage(y.reshape(-1)), list(y.shape))
+
+    def _plan(self, n, c, h, w, cp, impl):
+        key = (n, c, h, w, cp, impl)
+        p = self._plans.get(key)
+        if p is None:
+            L = _lib.load()
+            kc, _, kh, kw = self._qw_shape
+            p = L.i8ie_conv2d_plan_create(n, c, h, w, cp, kc, kh, kw, self._stride, self._pad, _r16(kc),
+                                          self._w_packed.data_ptr(), self._kc_pad, impl)
+            if not p:
+                raise I8ieError(f"conv2d_plan_create failed: {_lib.last_error()}")
+            self._plans[key] = p
+        return p
+
+    def __del__(self):
+        try:
+            L = _lib.load()
+            for p in self._plans.values():
+                L.i8ie_conv2d_plan_destroy(p)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _forward_u8(self, x, acc_out=None, impl=0):
+        # Conv2d::forward_prop(Tensor<u8>&&), conv2d.cc:100-142
+        L = _lib.load()
+        if len(x._shape) != 4:
+            raise RuntimeError("Conv2d expects a 4-d tensor")
+        n, c, h, w = x._shape
+        kc, cw, kh, kw = self._qw_shape
+        if c != cw:
+            raise RuntimeError(f"Conv2d: input has {c} channels, weight expects {cw}")
+        if h + 2 * self._pad < kh or w + 2 * self._pad < kw:
+            raise RuntimeError("Conv2d: kernel larger than padded input")
+        buf, cp = x._as_nhwc(n, c, h, w)
+        oh = (h - kh + 2 * self._pad) // self._stride + 1
+        ow = (w - kw + 2 * self._pad) // self._stride + 1
+        oc, _ = self._offsets(x._zp, x.scale(), True)
+        out_cp = _r16(kc)
+        out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=buf.device)
+        plan = self._plan(n, c, h, w, cp, impl)
+        flags = 1 if self.fuse_relu else 0
+        check(L.i8ie_conv2d_u8(plan, buf.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
+                               float(self._w_scale), float(self._scale), x._zp, self._zp, flags,
+                               acc_out.data_ptr() if acc_out is not None else None, _stream()), "conv2d_u8")
+        return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)

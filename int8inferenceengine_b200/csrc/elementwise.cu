@@ -1,0 +1,542 @@
+// HBM-bound kernels of the i8ie INT8 path: quantize / dequantize / down_scale /
+// min-max / relu / max-pool / layout glue / weight preparation.
+// All of them are streaming kernels: 128-bit coalesced accesses, several
+// independent loads in flight per thread, grids sized in multiples of the SM count.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace i8ie {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int stream_grid(int64_t work_items, int per_block) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)num_sms() * 8;  // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- A1 quantize f32 -> u8 (flat) -------------------------------------------
+// 16 elements per thread-iteration: 4 x 128-bit loads in flight, one 128-bit store.
+__global__ void __launch_bounds__(kThreads) quantize_flat_kernel(const float* __restrict__ x,
+                                                                 uint8_t* __restrict__ q, int64_t n,
+                                                                 float scale, float zpf, int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t nvec = vec_ok ? (n >> 4) : 0;
+  for (int64_t v = tid; v < nvec; v += nthreads) {
+    const float4* p = reinterpret_cast<const float4*>(x) + v * 4;
+    float4 f0 = ld_stream_f4(p), f1 = ld_stream_f4(p + 1), f2 = ld_stream_f4(p + 2), f3 = ld_stream_f4(p + 3);
+    uint4 o;
+    o.x = quant_u8_wrap(f0.x, scale, zpf) | (quant_u8_wrap(f0.y, scale, zpf) << 8) |
+          (quant_u8_wrap(f0.z, scale, zpf) << 16) | (quant_u8_wrap(f0.w, scale, zpf) << 24);
+    o.y = quant_u8_wrap(f1.x, scale, zpf) | (quant_u8_wrap(f1.y, scale, zpf) << 8) |
+          (quant_u8_wrap(f1.z, scale, zpf) << 16) | (quant_u8_wrap(f1.w, scale, zpf) << 24);
+    o.z = quant_u8_wrap(f2.x, scale, zpf) | (quant_u8_wrap(f2.y, scale, zpf) << 8) |
+          (quant_u8_wrap(f2.z, scale, zpf) << 16) | (quant_u8_wrap(f2.w, scale, zpf) << 24);
+    o.w = quant_u8_wrap(f3.x, scale, zpf) | (quant_u8_wrap(f3.y, scale, zpf) << 8) |
+          (quant_u8_wrap(f3.z, scale, zpf) << 16) | (quant_u8_wrap(f3.w, scale, zpf) << 24);
+    st_stream_u4(reinterpret_cast<uint4*>(q) + v, o);
+  }
+  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) q[i] = (uint8_t)quant_u8_wrap(x[i], scale, zpf);
+}
+
+// ---- A1 fused with NCHW(f32) -> NHWC(u8, pitch cp) ---------------------------
+// One thread per (pixel, 16-channel group): adjacent threads read adjacent pixels of
+// the same plane (coalesced) and write one 16-byte NHWC segment each.
+__global__ void __launch_bounds__(kThreads) quantize_nchw_nhwc_kernel(
+    const float* __restrict__ x, uint8_t* __restrict__ q, int n, int c, int hw, int cp, float scale,
+    float zpf, uint32_t zpb) {
+  const int groups = cp >> 4;
+  const int64_t total = (int64_t)n * hw * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = t % ((int64_t)n * hw);   // pixel fastest -> coalesced plane reads
+    const int g = (int)(t / ((int64_t)n * hw));
+    const int img = (int)(pix / hw);
+    const int p = (int)(pix % hw);
+    const float* src = x + ((int64_t)img * c) * hw + p;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ch = g * 16 + j * 4 + b;
+        const uint32_t v = (ch < c) ? quant_u8_wrap(__ldg(src + (int64_t)ch * hw), scale, zpf) : zpb;
+        word |= v << (8 * b);
+      }
+      w[j] = word;
+    }
+    *reinterpret_cast<uint4*>(q + pix * cp + g * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---- A5 dequantize u8 -> f32 (flat) -----------------------------------------
+__global__ void __launch_bounds__(kThreads) dequantize_flat_kernel(const uint8_t* __restrict__ q,
+                                                                   float* __restrict__ x, int64_t n,
+                                                                   float scale, int zp, int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t nvec = vec_ok ? (n >> 4) : 0;
+  for (int64_t v = tid; v < nvec; v += nthreads) {
+    const uint4 in = ld_stream_u4(reinterpret_cast<const uint4*>(q) + v);
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    float4* o = reinterpret_cast<float4*>(x) + v * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 f;
+      f.x = dequant_f32(w[j] & 0xff, zp, scale);
+      f.y = dequant_f32((w[j] >> 8) & 0xff, zp, scale);
+      f.z = dequant_f32((w[j] >> 16) & 0xff, zp, scale);
+      f.w = dequant_f32(w[j] >> 24, zp, scale);
+      st_stream_f4(o + j, f);
+    }
+  }
+  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) x[i] = dequant_f32(q[i], zp, scale);
+}
+
+__global__ void dequantize_rows_kernel(const uint8_t* __restrict__ q, float* __restrict__ x, int rows,
+                                       int cols, int pitch, float scale, int zp) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / cols), c = (int)(t % cols);
+    x[t] = dequant_f32(q[(int64_t)r * pitch + c], zp, scale);
+  }
+}
+
+// ---- A4 down_scale s32 -> u8 (flat) -------------------------------------------
+__global__ void __launch_bounds__(kThreads) downscale_flat_kernel(const int32_t* __restrict__ acc,
+                                                                  uint8_t* __restrict__ y, int64_t n,
+                                                                  float sa, float sb, float sc,
+                                                                  float zpf, int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t nvec = vec_ok ? (n >> 4) : 0;
+  for (int64_t v = tid; v < nvec; v += nthreads) {
+    const uint4* p = reinterpret_cast<const uint4*>(acc) + v * 4;
+    uint4 a[4] = {ld_stream_u4(p), ld_stream_u4(p + 1), ld_stream_u4(p + 2), ld_stream_u4(p + 3)};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = requant_u8((int)a[j].x, sa, sb, sc, zpf) | (requant_u8((int)a[j].y, sa, sb, sc, zpf) << 8) |
+             (requant_u8((int)a[j].z, sa, sb, sc, zpf) << 16) | (requant_u8((int)a[j].w, sa, sb, sc, zpf) << 24);
+    st_stream_u4(reinterpret_cast<uint4*>(y) + v, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) y[i] = (uint8_t)requant_u8(acc[i], sa, sb, sc, zpf);
+}
+
+// ---- A9 min/max reduction ------------------------------------------------------
+// warp shuffle -> block smem -> per-block partial -> the last block to finish folds
+// the partials (single launch, deterministic: min/max are order-independent).
+constexpr int kMinMaxMaxBlocks = 148 * 8;
+struct MinMaxWs {
+  unsigned int done;
+  unsigned int pad[3];
+  float mn[kMinMaxMaxBlocks];
+  float mx[kMinMaxMaxBlocks];
+};
+
+__device__ __forceinline__ void warp_minmax(float& mn, float& mx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const float* __restrict__ x, int64_t n,
+                                                          float* __restrict__ out2, MinMaxWs* ws,
+                                                          int vec_ok) {
+  __shared__ float smn[kThreads / 32], smx[kThreads / 32];
+  __shared__ bool is_last;
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nvec = vec_ok ? (n >> 4) : 0;  // 16 floats = 4 x float4 per thread-iteration
+  for (int64_t v = tid; v < nvec; v += nthreads) {
+    const float4* p = reinterpret_cast<const float4*>(x) + v * 4;
+    float4 f0 = ld_stream_f4(p), f1 = ld_stream_f4(p + 1), f2 = ld_stream_f4(p + 2), f3 = ld_stream_f4(p + 3);
+    mn = fminf(mn, fminf(fminf(fminf(f0.x, f0.y), fminf(f0.z, f0.w)), fminf(fminf(f1.x, f1.y), fminf(f1.z, f1.w))));
+    mn = fminf(mn, fminf(fminf(fminf(f2.x, f2.y), fminf(f2.z, f2.w)), fminf(fminf(f3.x, f3.y), fminf(f3.z, f3.w))));
+    mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(f0.x, f0.y), fmaxf(f0.z, f0.w)), fmaxf(fmaxf(f1.x, f1.y), fmaxf(f1.z, f1.w))));
+    mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(f2.x, f2.y), fmaxf(f2.z, f2.w)), fmaxf(fmaxf(f3.x, f3.y), fmaxf(f3.z, f3.w))));
+  }
+  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) {
+    mn = fminf(mn, x[i]);
+    mx = fmaxf(mx, x[i]);
+  }
+  warp_minmax(mn, mx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
+  __syncthreads();
+  if (wid == 0) {
+    mn = (lane < kThreads / 32) ? smn[lane] : FLT_MAX;
+    mx = (lane < kThreads / 32) ? smx[lane] : -FLT_MAX;
+    warp_minmax(mn, mx);
+    if (lane == 0) {
+      ws->mn[blockIdx.x] = mn;
+      ws->mx[blockIdx.x] = mx;
+      __threadfence();
+      const unsigned int prev = atomicAdd(&ws->done, 1u);
+      is_last = (prev == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    mn = FLT_MAX; mx = -FLT_MAX;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+      mn = fminf(mn, ((volatile float*)ws->mn)[b]);
+      mx = fmaxf(mx, ((volatile float*)ws->mx)[b]);
+    }
+    warp_minmax(mn, mx);
+    __syncthreads();
+    if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
+    __syncthreads();
+    if (wid == 0) {
+      mn = (lane < kThreads / 32) ? smn[lane] : FLT_MAX;
+      mx = (lane < kThreads / 32) ? smx[lane] : -FLT_MAX;
+      warp_minmax(mn, mx);
+      if (lane == 0) {
+        out2[0] = mn;
+        out2[1] = mx;
+        ws->done = 0;  // workspace is reusable without re-zeroing
+      }
+    }
+  }
+}
+
+// ---- A10 relu<u8> --------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) relu_flat_kernel(const uint8_t* __restrict__ x,
+                                                             uint8_t* __restrict__ y, int64_t n,
+                                                             uint32_t zp4, int vec_ok) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nvec = vec_ok ? (n >> 4) : 0;
+  for (int64_t v = tid; v < nvec; v += nthreads) {
+    uint4 a = ld_stream_u4(reinterpret_cast<const uint4*>(x) + v);
+    a.x = __vmaxu4(a.x, zp4); a.y = __vmaxu4(a.y, zp4); a.z = __vmaxu4(a.z, zp4); a.w = __vmaxu4(a.w, zp4);
+    st_stream_u4(reinterpret_cast<uint4*>(y) + v, a);
+  }
+  const uint8_t z = (uint8_t)(zp4 & 0xff);
+  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) y[i] = x[i] > z ? x[i] : z;
+}
+
+// ---- A11 max_pool2d<u8>, NHWC --------------------------------------------------
+// One thread per (output pixel, 16-channel group): k*k 128-bit loads, byte-wise max.
+__global__ void __launch_bounds__(kThreads) maxpool_nhwc_kernel(const uint8_t* __restrict__ x,
+                                                                uint8_t* __restrict__ y, int n, int h,
+                                                                int w, int c, int cp, int ks, int st,
+                                                                int oh, int ow, int out_nchw) {
+  const int groups = cp >> 4;
+  const int64_t total = (int64_t)n * oh * ow * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % groups);
+    int64_t r = t / groups;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh);
+    const int img = (int)(r / oh);
+    uint4 m = make_uint4(0, 0, 0, 0);  // min<u8_t>() == 0 (functional.cc:33-35)
+    for (int a = 0; a < ks; ++a)
+      for (int b = 0; b < ks; ++b) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+            x + (((int64_t)img * h + (oy * st + a)) * w + (ox * st + b)) * cp + g * 16));
+        m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
+      }
+    if (!out_nchw) {
+      *reinterpret_cast<uint4*>(y + (((int64_t)img * oh + oy) * ow + ox) * cp + g * 16) = m;
+    } else {
+      const uint32_t wds[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int ch = g * 16 + j;
+        if (ch < c) y[(((int64_t)img * c + ch) * oh + oy) * ow + ox] = (uint8_t)(wds[j >> 2] >> (8 * (j & 3)));
+      }
+    }
+  }
+}
+
+// ---- layout glue ---------------------------------------------------------------
+__global__ void u8_nchw_to_nhwc_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int n,
+                                       int c, int hw, int cp, uint32_t padv) {
+  const int groups = cp >> 4;
+  const int64_t npix = (int64_t)n * hw;
+  const int64_t total = npix * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = t % npix;
+    const int g = (int)(t / npix);
+    const int img = (int)(pix / hw), p = (int)(pix % hw);
+    const uint8_t* src = x + ((int64_t)img * c) * hw + p;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ch = g * 16 + j * 4 + b;
+        const uint32_t v = (ch < c) ? (uint32_t)__ldg(src + (int64_t)ch * hw) : padv;
+        word |= v << (8 * b);
+      }
+      w[j] = word;
+    }
+    *reinterpret_cast<uint4*>(y + pix * cp + g * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void u8_nhwc_to_nchw_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int n,
+                                       int c, int hw, int cp) {
+  const int64_t total = (int64_t)n * c * hw;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(t % hw);
+    int64_t r = t / hw;
+    const int ch = (int)(r % c);
+    const int img = (int)(r / c);
+    y[t] = x[((int64_t)img * hw + p) * cp + ch];
+  }
+}
+
+// ---- A2b / A3 offsets ----------------------------------------------------------
+// One warp per output row. t is a sequential fp32 sum of the INTEGERS zp*w[k]; while
+// zp * sum|w| < 2^24 every partial sum is an exactly representable integer, so the
+// sequential fp32 result equals the exact integer sum and the warp computes it in
+// parallel. Otherwise lane 0 replays the reference's sequential fp32 loop.
+__global__ void __launch_bounds__(kThreads) zp_offsets_kernel(const int8_t* __restrict__ qw,
+                                                              const int8_t* __restrict__ qb, int n,
+                                                              int k, int zp, float in_scale,
+                                                              int is_conv, int32_t* __restrict__ oc,
+                                                              float* __restrict__ bias_f) {
+  const int row = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int8_t* wr = qw + (int64_t)row * k;
+  long long s = 0, sabs = 0;
+  for (int i = lane; i < k; i += 32) {
+    const int v = wr[i];
+    s += v;
+    sabs += (v < 0) ? -v : v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sabs += __shfl_xor_sync(0xffffffffu, sabs, o);
+  }
+  if (lane != 0) return;
+  float t;
+  if ((long long)zp * sabs < (1ll << 24)) {
+    t = (float)((long long)zp * s);
+  } else {
+    t = 0.f;
+    for (int i = 0; i < k; ++i) t = __fadd_rn(t, __int2float_rn(zp * (int)wr[i]));
+  }
+  const float b = __fdiv_rn(__int2float_rn((int)qb[row]), in_scale);
+  if (is_conv) {
+    oc[row] = __float2int_rz(__fsub_rn(b, t));  // conv2d.cc:123
+    bias_f[row] = 0.f;
+  } else {
+    oc[row] = __float2int_rz(-t);               // fully_connected.cc:37
+    bias_f[row] = b;                            // fully_connected.cc:44
+  }
+}
+
+__global__ void pack_conv_weight_kernel(const int8_t* __restrict__ qw, int8_t* __restrict__ wp, int kc,
+                                        int c, int kh, int kw, int kc_pad, int cp) {
+  const int64_t total = (int64_t)kc_pad * kh * kw * cp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(t % cp);
+    int64_t r = t / cp;
+    const int x = (int)(r % kw); r /= kw;
+    const int y = (int)(r % kh);
+    const int o = (int)(r / kh);
+    wp[t] = (o < kc && ch < c) ? qw[(((int64_t)o * c + ch) * kh + y) * kw + x] : (int8_t)0;
+  }
+}
+
+}  // namespace
+}  // namespace i8ie
+
+using namespace i8ie;
+
+extern "C" {
+
+const char* i8ie_last_error(void) { return g_err; }
+const char* i8ie_version(void) { return "i8ie_sm100 0.1 (sm_100a)"; }
+int64_t i8ie_launch_count(void) { return g_launches.load(); }
+
+int i8ie_device_check(void) {
+  int dev = 0;
+  I8IE_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  I8IE_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  I8IE_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10 || minor != 0) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+    return I8IE_ENOTSM100;
+  }
+  return I8IE_OK;
+}
+
+int i8ie_quantize_f32_u8(const float* x, uint8_t* q, int64_t n, float scale, int zp, void* stream) {
+  I8IE_REQUIRE(n >= 0 && zp >= 0 && zp <= 255, "quantize: bad n/zp");
+  if (n == 0) return I8IE_OK;
+  const int vec = aligned16(x) && aligned16(q);
+  quantize_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, q, n, scale, (float)zp, vec);
+  return check_launch("quantize_flat_kernel");
+}
+
+int i8ie_quantize_nchw_f32_nhwc_u8(const float* x, uint8_t* q, int n, int c, int h, int w, int cp,
+                                   float scale, int zp, void* stream) {
+  I8IE_REQUIRE(cp % 16 == 0 && cp >= c && zp >= 0 && zp <= 255 && aligned16(q), "quantize_nhwc: bad cp/zp/alignment");
+  const int64_t items = (int64_t)n * h * w * (cp / 16);
+  if (items == 0) return I8IE_OK;
+  quantize_nchw_nhwc_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, q, n, c, h * w, cp, scale, (float)zp, (uint32_t)zp);
+  return check_launch("quantize_nchw_nhwc_kernel");
+}
+
+int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, int zp, void* stream) {
+  I8IE_REQUIRE(n >= 0, "dequantize: bad n");
+  if (n == 0) return I8IE_OK;
+  const int vec = aligned16(x) && aligned16(q);
+  dequantize_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      q, x, n, scale, zp, vec);
+  return check_launch("dequantize_flat_kernel");
+}
+
+int i8ie_dequantize_rows_u8_f32(const uint8_t* q, float* x, int rows, int cols, int pitch, float scale,
+                                int zp, void* stream) {
+  I8IE_REQUIRE(rows >= 0 && cols >= 0 && pitch >= cols, "dequantize_rows: bad shape");
+  if ((int64_t)rows * cols == 0) return I8IE_OK;
+  dequantize_rows_kernel<<<stream_grid((int64_t)rows * cols, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      q, x, rows, cols, pitch, scale, zp);
+  return check_launch("dequantize_rows_kernel");
+}
+
+int i8ie_downscale_s32_u8(const int32_t* acc, uint8_t* y, int64_t n, float sa, float sb, float sc,
+                          int zp_c, void* stream) {
+  I8IE_REQUIRE(n >= 0, "downscale: bad n");
+  if (n == 0) return I8IE_OK;
+  const int vec = aligned16(acc) && aligned16(y);
+  downscale_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      acc, y, n, sa, sb, sc, (float)zp_c, vec);
+  return check_launch("downscale_flat_kernel");
+}
+
+int64_t i8ie_minmax_workspace_bytes(void) { return (int64_t)sizeof(MinMaxWs); }
+
+int i8ie_minmax_f32(const float* x, int64_t n, float* out2, void* workspace, void* stream) {
+  I8IE_REQUIRE(n > 0 && workspace != nullptr, "minmax: n must be > 0 and workspace non-null");
+  int grid = stream_grid((n + 15) / 16, kThreads);
+  if (grid > kMinMaxMaxBlocks) grid = kMinMaxMaxBlocks;
+  minmax_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, n, out2, (MinMaxWs*)workspace, aligned16(x));
+  return check_launch("minmax_kernel");
+}
+
+// calibrator.cc:28-35
+int i8ie_range_from_minmax_host(float mn, float mx, float* scale_host, uint8_t* zp_host) {
+  float out_min = fminf(mn, 0.f), out_max = fmaxf(mx, 0.f);
+  const double q = (double)(255 * (0 - out_min)) / ((double)(out_max - out_min) + 1e-09);
+  const uint8_t zp = (uint8_t)(int32_t)q;
+  float s = (zp == 0) ? (out_max - out_min) / 255 : (0 - out_min) / zp;
+  if (s == 0) s = 1;
+  *scale_host = s;
+  *zp_host = zp;
+  return I8IE_OK;
+}
+
+int i8ie_relu_u8(const uint8_t* x, uint8_t* y, int64_t n, int zp, void* stream) {
+  I8IE_REQUIRE(n >= 0 && zp >= 0 && zp <= 255, "relu: bad n/zp");
+  if (n == 0) return I8IE_OK;
+  const uint32_t z = (uint32_t)zp;
+  relu_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, y, n, z | (z << 8) | (z << 16) | (z << 24), aligned16(x) && aligned16(y));
+  return check_launch("relu_flat_kernel");
+}
+
+int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int c, int cp, int ksize,
+                         int stride, int out_nchw, void* stream) {
+  I8IE_REQUIRE(cp % 16 == 0 && cp >= c && ksize >= 1 && stride >= 1 && h >= ksize && w >= ksize &&
+                   aligned16(x) && (out_nchw || aligned16(y)),
+               "maxpool: bad shape/alignment");
+  const int oh = (h - ksize) / stride + 1, ow = (w - ksize) / stride + 1;
+  const int64_t items = (int64_t)n * oh * ow * (cp / 16);
+  if (items == 0) return I8IE_OK;
+  maxpool_nhwc_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
+  return check_launch("maxpool_nhwc_kernel");
+}
+
+int i8ie_u8_nchw_to_nhwc(const uint8_t* x, uint8_t* y, int n, int c, int h, int w, int cp, int pad_value,
+                         void* stream) {
+  I8IE_REQUIRE(cp % 16 == 0 && cp >= c && aligned16(y), "nchw_to_nhwc: bad cp/alignment");
+  const int64_t items = (int64_t)n * h * w * (cp / 16);
+  if (items == 0) return I8IE_OK;
+  u8_nchw_to_nhwc_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, y, n, c, h * w, cp, (uint32_t)(pad_value & 0xff));
+  return check_launch("u8_nchw_to_nhwc_kernel");
+}
+
+int i8ie_u8_nhwc_to_nchw(const uint8_t* x, uint8_t* y, int n, int c, int h, int w, int cp, void* stream) {
+  I8IE_REQUIRE(cp >= c, "nhwc_to_nchw: bad cp");
+  const int64_t items = (int64_t)n * c * h * w;
+  if (items == 0) return I8IE_OK;
+  u8_nhwc_to_nchw_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(x, y, n, c, h * w, cp);
+  return check_launch("u8_nhwc_to_nchw_kernel");
+}
+
+// layer.cc:6-26 (host, once per model)
+int i8ie_quantize_weight_host(const float* w, int64_t nw, const float* b, int64_t nb, int8_t* qw,
+                              int8_t* qb, float* scale_host) {
+  float mx = -FLT_MAX, mn = FLT_MAX;
+  for (int64_t i = 0; i < nw; ++i) { mn = (w[i] < mn) ? w[i] : mn; mx = (mx < w[i]) ? w[i] : mx; }
+  for (int64_t i = 0; i < nb; ++i) { mn = (b[i] < mn) ? b[i] : mn; mx = (mx < b[i]) ? b[i] : mx; }
+  const float scale = (mx - mn) / 127;
+  for (int64_t i = 0; i < nw; ++i) qw[i] = (int8_t)(int32_t)(w[i] / scale);
+  for (int64_t i = 0; i < nb; ++i) qb[i] = (int8_t)(int32_t)(b[i] / scale);
+  *scale_host = scale;
+  return I8IE_OK;
+}
+
+int i8ie_zp_offsets(const int8_t* qw, const int8_t* qb, int n, int k, int in_zp, float in_scale,
+                    int is_conv, int32_t* oc, float* bias_f, void* stream) {
+  I8IE_REQUIRE(n > 0 && k > 0 && in_zp >= 0 && in_zp <= 255, "zp_offsets: bad shape/zp");
+  const int rows_per_block = kThreads / 32;
+  zp_offsets_kernel<<<(n + rows_per_block - 1) / rows_per_block, kThreads, 0, (cudaStream_t)stream>>>(
+      qw, qb, n, k, in_zp, in_scale, is_conv, oc, bias_f);
+  return check_launch("zp_offsets_kernel");
+}
+
+int i8ie_pack_conv_weight(const int8_t* qw_oihw, int8_t* w_packed, int kc, int c, int kh, int kw,
+                          int kc_pad, int cp, void* stream) {
+  I8IE_REQUIRE(kc_pad >= kc && cp >= c && cp % 16 == 0, "pack_conv_weight: bad padding");
+  const int64_t items = (int64_t)kc_pad * kh * kw * cp;
+  pack_conv_weight_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      qw_oihw, w_packed, kc, c, kh, kw, kc_pad, cp);
+  return check_launch("pack_conv_weight_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// SIMT (dp4a) implicit-GEMM kernel for the shapes the tcgen05 path does not take
+// (tiny / oddly-shaped layers, forced impl=1) and the reference against which the
+// tensor-core kernels are unit-tested on the device. Same fused epilogue as the
+// tcgen05 kernels: + oc, [fc float bias], requantise, [relu], u8 NHWC store.
+//
+// conv (conv2d.cc:100-142): A[m][k] is gathered on the fly from the NHWC input
+// (m = (img, oy, ox), k = (ky, kx, c)); spatially out-of-range taps are filled with
+// the input zero_point exactly like im2col_tile (conv2d.cc:24-25). No im2col
+// buffer is materialised. FC (fully_connected.cc:22-52) is the same kernel with a
+// 1x1 "image" per row.
+#include "common.cuh"
+#include "gemm_api.cuh"
+
+namespace i8ie {
+namespace {
+
+constexpr int BM = 64, BN = 64, NT = 256;
+
+__global__ void __launch_bounds__(NT) simt_igemm_kernel(const GemmGeom g, const uint8_t* __restrict__ x,
+                                                       const int8_t* __restrict__ w,
+                                                       uint8_t* __restrict__ y, const EpiParams ep,
+                                                       const uint32_t zp_in4) {
+  __shared__ uint4 sA[2][BM];
+  __shared__ uint4 sB[2][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  // loader roles: threads [0,64) fetch one A row chunk, [64,128) one B row chunk
+  const bool isA = tid < BM, isB = (tid >= BM) && (tid < BM + BN);
+  const int r = tid & 63;
+  const int cgroups = g.cp >> 4;
+  const int ksteps = g.kh * g.kw * cgroups;
+
+  const uint8_t* abase = nullptr;
+  int iy0 = 0, ix0 = 0;
+  bool mvalid = false;
+  const int8_t* wrow = nullptr;
+  if (isA) {
+    const int m = m0 + r;
+    mvalid = m < g.M;
+    if (mvalid) {
+      const int ox = m % g.ow;
+      const int t = m / g.ow;
+      const int oy = t % g.oh;
+      const int img = t / g.oh;
+      iy0 = oy * g.stride - g.pad;
+      ix0 = ox * g.stride - g.pad;
+      abase = x + (size_t)img * g.h * g.w * g.cp;
+    }
+  } else if (isB) {
+    const int n = n0 + r;
+    if (n < g.n_pad) wrow = w + (size_t)n * g.ldw;
+  }
+
+  int ky = 0, kx = 0, cg = 0;  // loader's running (tap, channel-group) position
+  auto fetch = [&]() -> uint4 {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (isA) {
+      v = make_uint4(zp_in4, zp_in4, zp_in4, zp_in4);
+      const int iy = iy0 + ky, ix = ix0 + kx;
+      if (mvalid && iy >= 0 && iy < g.h && ix >= 0 && ix < g.w)
+        v = __ldg(reinterpret_cast<const uint4*>(abase + ((size_t)iy * g.w + ix) * g.cp + cg * 16));
+    } else if (isB) {
+      if (wrow) v = __ldg(reinterpret_cast<const uint4*>(wrow + (size_t)(ky * g.kw + kx) * g.cp + cg * 16));
+    }
+    if (++cg == cgroups) { cg = 0; if (++kx == g.kw) { kx = 0; ++ky; } }
+    return v;
+  };
+
+  int32_t acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+  uint4 pre = fetch();
+  if (isA) sA[0][r] = pre; else if (isB) sB[0][r] = pre;
+  __syncthreads();
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int cur = ks & 1;
+    if (ks + 1 < ksteps) pre = fetch();
+    uint4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = sA[cur][ty + 16 * i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = sB[cur][tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int32_t s = acc[i][j];
+        s = dp4a_u8s8(a[i].x, b[j].x, s);
+        s = dp4a_u8s8(a[i].y, b[j].y, s);
+        s = dp4a_u8s8(a[i].z, b[j].z, s);
+        s = dp4a_u8s8(a[i].w, b[j].w, s);
+        acc[i][j] = s;
+      }
+    if (ks + 1 < ksteps) {
+      if (isA) sA[cur ^ 1][r] = pre; else if (isB) sB[cur ^ 1][r] = pre;
+    }
+    __syncthreads();
+  }
+
+  // fused epilogue
+  const float zpf = (float)ep.zp_out;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx + 16 * j;
+    if (n >= g.out_cp) continue;
+    const bool real = n < g.N;
+    const int32_t ocn = real ? __ldg(ep.oc + n) : 0;
+    const float bf = (real && ep.bias_f) ? __ldg(ep.bias_f + n) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty + 16 * i;
+      if (m >= g.M) continue;
+      uint32_t q = (uint32_t)ep.zp_out;  // pad lanes carry the zero point
+      if (real) {
+        int32_t v = acc[i][j] + ocn;
+        if (ep.bias_f) v = fc_bias_add(v, bf);
+        if (ep.acc_out) ep.acc_out[(size_t)m * g.N + n] = v;
+        q = requant_u8(v, ep.sa, ep.sb, ep.sc, zpf);
+        if (ep.relu) q = max(q, (uint32_t)ep.zp_out);
+      }
+      y[(size_t)m * g.out_cp + n] = (uint8_t)q;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_simt_igemm(const GemmGeom& g, const uint8_t* x, const int8_t* w, uint8_t* y,
+                      const EpiParams& ep, int zp_in, cudaStream_t stream) {
+  const uint32_t z = (uint32_t)(zp_in & 0xff);
+  dim3 grid((g.M + BM - 1) / BM, (g.out_cp + BN - 1) / BN);
+  simt_igemm_kernel<<<grid, NT, 0, stream>>>(g, x, w, y, ep, z | (z << 8) | (z << 16) | (z << 24));
+  return check_launch("simt_igemm_kernel");
+}
+
+}  // namespace i8ie

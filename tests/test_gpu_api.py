@@ -1,0 +1,152 @@
+"""-m gpu: the reference's own unit tests (unittest/test_*.py), re-stated against the B200
+backend through the unchanged `i8ie` surface. Same inputs / tolerances as the originals."""
+import numpy as np
+import pytest
+import torch
+
+import i8ie
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(shape, lo=-100, hi=100, seed=0):
+    return np.random.default_rng(seed).uniform(lo, hi, size=shape).astype(np.float32)
+
+
+# unittest/test_quantization.py:13-23
+def test_quantize_roundtrip():
+    a = rnd((4, 4), -1, 1)
+    q = i8ie.quantize(i8ie.tensor(a), 0.025, 100)
+    assert np.allclose(a, (q.numpy().astype(np.float32) - 100) * 0.025, atol=0.1)
+    assert np.allclose(a, i8ie.dequantize(q).numpy(), atol=0.1)
+    assert q.scale == pytest.approx(0.025) and q.zero_point == 100
+
+
+# unittest/test_refcount.py:11-45
+def test_refcount_semantics():
+    t = i8ie.tensor(rnd((4, 4)))
+    t = t
+    assert t.data.ref_count() == 1
+    b = t
+    c = t
+    c = 0
+    assert t.data.ref_count() == 1 and b.data.ref_count() == 1
+    t.reshape(-1, 2)
+    c = t.reshape(4, -1)
+    assert t.data.ref_count() == 2 and c.data.ref_count() == 2
+    fc = i8ie.Linear(4, 4)
+    t = i8ie.tensor(rnd((4, 4)))
+    fc(t)
+    t = fc(t)
+    u = fc(t)
+    t = fc(u)
+    assert t.data.ref_count() == 1 and u.data.ref_count() == 1
+
+
+# unittest/test_tensor_ops.py:13-46 (with the missing `shape` argument supplied)
+def test_tensor_ops():
+    a = rnd((3, 4, 5))
+    t = i8ie.tensor(a)
+    assert np.array_equal(t.numpy(), a)
+    assert np.array_equal(t.reshape(-1, 5).numpy(), a.reshape(-1, 5))
+    assert t.reshape(2, -1).shape == (2, 30)
+    assert np.isclose(t.sum(), a.sum())
+    with pytest.raises(RuntimeError):
+        t.reshape(-1, -1)
+    with pytest.raises(RuntimeError):
+        t.reshape(7, -1)
+    with pytest.raises(RuntimeError):
+        t.reshape(0, 60)
+    x = i8ie.tensor(np.array([[1, 5, 2], [9, 0, 3]]))
+    assert np.array_equal(i8ie.argmax(x, 1).numpy(), np.array([1, 0], np.float32))
+    p = i8ie.tensor(np.array([1, 2, 3, 4]))
+    tgt = i8ie.tensor(np.array([1, 0, 3, 0]))
+    assert (p == tgt).sum() == 2.0           # notebooks: (p == target).sum()
+    img = rnd((2, 3, 8, 8))
+    got = i8ie.max_pool2d(i8ie.tensor(img), 2, 2).numpy()
+    exp = torch.nn.functional.max_pool2d(torch.tensor(img), 2, 2).numpy()
+    assert np.array_equal(got, exp)
+    assert np.array_equal(i8ie.relu(i8ie.tensor(img)).numpy(), np.maximum(img, 0))
+    # torch CPU tensors are accepted like ndarrays (numpy array interface)
+    assert np.array_equal(i8ie.tensor(torch.tensor(img)).numpy(), img)
+
+
+# unittest/test_layers.py:13-71 (fp32 layers vs torch, atol 0.1)
+def test_fp32_layers_vs_torch():
+    lin = torch.nn.Linear(800, 500)
+    my = i8ie.Linear(800, 500)
+    my.load_weight(lin.weight.detach().numpy())
+    my.load_bias(lin.bias.detach().numpy())
+    a = rnd((200, 800), -1, 1)
+    assert np.allclose(my(i8ie.tensor(a)).numpy(), lin(torch.tensor(a)).detach().numpy(), atol=0.1)
+    for (hw, k, s, p) in [(22, 3, 1, 0), (22, 3, 1, 1), (50, 3, 7, 3)]:
+        conv = torch.nn.Conv2d(10, 20, k, stride=s, padding=p)
+        mc = i8ie.Conv2d(10, 20, k, stride=s, padding=p)
+        mc.load_weight(conv.weight.detach().numpy())
+        mc.load_bias(conv.bias.detach().numpy())
+        a = rnd((30, 10, hw, hw), -1, 1)
+        assert np.allclose(mc(i8ie.tensor(a)).numpy(), conv(torch.tensor(a)).detach().numpy(), atol=0.1)
+
+
+# unittest/test_quantized_layer.py:45-95 with synthetic weights instead of conv28.pt
+def test_quantized_lenet_layer_by_layer():
+    from int8inferenceengine_b200 import workloads as W
+    from int8inferenceengine_b200.runner import build_module
+    sd = W.make_weights("lenet", 0)
+    m = build_module("lenet", sd, calib=rnd((100, 1, 28, 28), -2, 2, seed=1))
+    x = rnd((10, 1, 28, 28), -2, 2, seed=2)
+    tsd = {k: torch.tensor(v) for k, v in sd.items()}
+    F = torch.nn.functional
+
+    def close(a, b):
+        return np.isclose(a, b, rtol=0.3).sum() > 0.8 * a.size
+
+    q = m.conv1(i8ie.quantize(i8ie.tensor(x), 0.025, 127))
+    y = F.conv2d(torch.tensor(x), tsd["conv1.weight"], tsd["conv1.bias"])
+    assert close(y.numpy(), i8ie.dequantize(q).numpy())
+    q = i8ie.max_pool2d(q, 2, 2)
+    y = F.max_pool2d(y, 2, 2)
+    assert close(y.numpy(), i8ie.dequantize(q).numpy())
+    q = m.conv2(q)
+    y = F.conv2d(y, tsd["conv2.weight"], tsd["conv2.bias"])
+    assert close(y.numpy(), i8ie.dequantize(q).numpy())
+    q = i8ie.max_pool2d(q, 2, 2).reshape(-1, 800)
+    y = F.max_pool2d(y, 2, 2).reshape(-1, 800)
+    q = i8ie.relu(m.fc1(q))
+    y = F.relu(F.linear(y, tsd["fc1.weight"], tsd["fc1.bias"]))
+    assert close(y.numpy(), i8ie.dequantize(q).numpy())
+    q = m.fc2(q)
+    y = F.linear(y, tsd["fc2.weight"], tsd["fc2.bias"])
+    assert close(y.numpy(), i8ie.dequantize(q).numpy())
+
+
+def test_calibrator_matches_reference_when_deterministic():
+    """<=1000 calibration outputs: the reference's range is deterministic, incl.
+    the zero-filled-tail quirk; golden values come from the compiled reference."""
+    from conftest import load_golden
+    g = load_golden("kat_get_range")
+    for tag in ["full1000", "lt1000", "all_pos", "all_neg", "all_zero", "tiny", "wide", "lt1000_neg"]:
+        a = g[f"{tag}_samples"]
+        L = i8ie.Linear(10, 10)
+        L.load_weight(np.eye(10, dtype=np.float32))
+        L.load_bias(np.zeros(10, np.float32))
+        L.prepare()
+        L(i8ie.tensor(a))
+        L.convert()
+        o = L(i8ie.quantize(i8ie.tensor(a[:1]), 0.025, 127))
+        es, ez = g[f"{tag}_sz"]
+        assert np.float32(o.scale) == np.float32(es) and o.zero_point == int(ez), tag
+
+
+def test_error_paths():
+    L = i8ie.Linear(4, 4)
+    L.convert()
+    with pytest.raises(RuntimeError):
+        L(i8ie.tensor(rnd((2, 4))))          # fp32 forward after convert (reference: null deref)
+    with pytest.raises(RuntimeError):
+        L.load_weight(np.zeros((4, 4), np.float32))   # layer.h:16-18
+    L2 = i8ie.Linear(4, 4)
+    with pytest.raises(RuntimeError):
+        L2(i8ie.quantize(i8ie.tensor(rnd((2, 4))), 0.025, 127))   # u8 forward before convert
+    with pytest.raises(RuntimeError):
+        i8ie.Conv2d(1, 1, 3, stride=0)       # conv2d.h:12-14

@@ -1,0 +1,130 @@
+"""-m gpu parity: conv2d / fully-connected through the C ABI vs the oracle and the golden
+vectors of the compiled reference. Bit-exact: u8 outputs AND s32 accumulators."""
+import numpy as np
+import pytest
+import torch
+
+from int8inferenceengine_b200 import backend as B
+from oracle import port
+
+from conftest import load_golden
+from gpu_utils import make_layer, u8_tensor_from_nchw
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = [1, 0]   # 1 = forced SIMT dp4a kernel, 0 = auto (tcgen05 where eligible)
+
+
+def run_conv(L, q, in_scale, in_zp, impl, want_acc=True):
+    n, c, h, w = q.shape
+    kc, _, kh, kw = L._qw_shape
+    oh = (h - kh + 2 * L._pad) // L._stride + 1
+    ow = (w - kw + 2 * L._pad) // L._stride + 1
+    acc = torch.empty(n * oh * ow * kc, dtype=torch.int32, device="cuda") if want_acc else None
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=impl)
+    return out.numpy(), (acc.cpu().numpy().reshape(n, oh * ow, kc) if want_acc else None)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["k5", "k11s4p2", "k5p2", "k3s7p3", "k3p1", "k3p1_c64"])
+def test_conv_golden(tag, impl):
+    g = load_golden("kat_conv")
+    n, c, h, w_, kc, k, s, p = [int(v) for v in g[f"{tag}_geom"]]
+    os_, oz = g[f"{tag}_sz"]
+    L = make_layer("conv", g[f"{tag}_w"], g[f"{tag}_b"], (os_, int(oz)), s, p)
+    out, _ = run_conv(L, g[f"{tag}_qin"], 0.025, 127, impl)
+    assert np.array_equal(out, g[f"{tag}_out"])
+    out2, _ = run_conv(L, g[f"{tag}_qin2"], 0.031, 90, impl)
+    assert np.array_equal(out2, g[f"{tag}_out2"])
+
+
+GEOMS = [  # n, c, h, w, kc, k, stride, pad
+    (1, 1, 5, 5, 1, 1, 1, 0), (2, 3, 32, 32, 20, 5, 1, 0), (2, 20, 28, 28, 50, 5, 1, 0),
+    (3, 50, 12, 12, 120, 5, 1, 0), (2, 3, 67, 67, 32, 11, 4, 2), (2, 32, 7, 7, 64, 5, 1, 2),
+    (2, 64, 13, 13, 96, 3, 1, 1), (1, 96, 27, 27, 256, 5, 1, 2), (2, 256, 13, 13, 384, 3, 1, 1),
+    (5, 16, 9, 8, 24, 3, 2, 1), (2, 17, 6, 10, 33, 4, 3, 2), (1, 128, 8, 8, 128, 3, 1, 1),
+    (130, 8, 3, 3, 8, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_vs_oracle(geom, impl):
+    n, c, h, w_, kc, k, s, p = geom
+    rng = np.random.default_rng(sum(geom))
+    a = np.sqrt(6.0 / (c * k * k))
+    w = rng.uniform(-a, a, size=(kc, c, k, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(kc,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(n, c, h, w_), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0293), int(rng.integers(0, 256))
+    out_scale, out_zp = np.float32(0.061), int(rng.integers(60, 190))
+    L = make_layer("conv", w, b, (out_scale, out_zp), s, p)
+    qw, qb, ws = port.quantize_weight(w, b)
+    assert np.array_equal(L.q_weight().numpy(), qw) and np.array_equal(L.q_bias().numpy(), qb)
+    exp, exp_acc = port.conv2d_u8(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    out, acc = run_conv(L, q, in_scale, in_zp, impl)
+    assert np.array_equal(acc, exp_acc), "s32 accumulators differ"
+    assert np.array_equal(out, exp), "requantised u8 differ"
+    # fused relu epilogue == separate relu<u8>
+    L.fuse_relu = True
+    out_r, _ = run_conv(L, q, in_scale, in_zp, impl, want_acc=False)
+    assert np.array_equal(out_r, port.relu_u8(exp, out_zp))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_linear_golden(tag, impl):
+    g = load_golden("kat_linear")
+    os_, oz = g[f"{tag}_sz"]
+    L = make_layer("fc", g[f"{tag}_w"], g[f"{tag}_b"], (os_, int(oz)))
+    x = u8_tensor_from_nchw(g[f"{tag}_qin"], 0.025, 127)
+    out = L._forward_u8(x, impl=impl)
+    assert np.array_equal(out.numpy(), g[f"{tag}_out"])
+    assert np.array_equal(B.dequantize(out).numpy(), g[f"{tag}_deq"])
+
+
+FC_SHAPES = [(1, 1, 1), (100, 784, 10), (7, 300, 24), (3, 65, 130), (100, 7680, 10), (16, 9216, 512),
+             (130, 4096, 4096), (257, 512, 300), (5, 4096, 10), (64, 800, 500)]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", FC_SHAPES)
+def test_linear_vs_oracle(shape, impl):
+    m, k, n = shape
+    rng = np.random.default_rng(m + k + n)
+    a = np.sqrt(6.0 / k)
+    w = rng.uniform(-a, a, size=(n, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(n,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(m, k), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0518), int(rng.integers(0, 256))
+    out_scale, out_zp = np.float32(0.18), int(rng.integers(60, 190))
+    L = make_layer("fc", w, b, (out_scale, out_zp))
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.linear_u8(q, qw, qb, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    acc = torch.empty(m * n, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=impl)
+    assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc), "s32 accumulators differ"
+    assert np.array_equal(out.numpy(), exp)
+    L.fuse_relu = True
+    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=impl)
+    assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
+
+
+def test_fc_bias_float_roundtrip_above_2_24():
+    """fully_connected.cc:44 adds the bias in fp32 on the s32 accumulator: bits above 2^24 are
+    lost exactly as in the reference. Large K with saturated operands reaches that range."""
+    m, k, n = 4, 9216, 16
+    w = np.full((n, k), 1.0, np.float32)
+    w[::2] *= -1
+    w[0, :5] = 0.013
+    b = np.linspace(-1, 1, n).astype(np.float32)
+    q = np.full((m, k), 255, np.uint8)
+    q[1] = 200
+    L = make_layer("fc", w, b, (np.float32(3000.0), 128))
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.linear_u8(q, qw, qb, np.float32(0.025), 3, ws, np.float32(3000.0), 128, want_acc=True)
+    assert np.abs(exp_acc).max() > 2 ** 24
+    acc = torch.empty(m * n, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, 0.025, 3), acc_out=acc)
+    assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc)
+    assert np.array_equal(out.numpy(), exp)

@@ -1,0 +1,92 @@
+"""-m gpu parity: whole topologies through the public `i8ie` API vs the golden vectors of
+the compiled reference (per-op u8 activations bit-exact, logits bit-equal), plus
+size-independent properties at the BASELINE batch sizes."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import i8ie
+from int8inferenceengine_b200 import workloads as W
+from int8inferenceengine_b200.runner import build_module
+from oracle import models
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _qp(g):
+    return {str(n): (np.float32(s), int(z)) for n, s, z in zip(g["qp_names"], g["qp_scale"], g["qp_zp"])}
+
+
+@pytest.mark.parametrize("topo", ["fc_mnist", "lenet", "simple_conv", "mini_alex"])
+def test_net_golden(topo):
+    g = load_golden(f"net_{topo}")
+    m = build_module(topo, W.make_weights(topo, 0), qparams=_qp(g))
+    m.record = []
+    x = W.make_images(topo, int(g["batch"]), 2)
+    logits = m(i8ie.tensor(x)).numpy()
+    keys = sorted(k for k in g.files if k.startswith("op"))
+    # op00 is the quantised input (module.py:20); the recorded ops follow
+    assert np.array_equal(i8ie.quantize(i8ie.tensor(x), 0.025, 127).numpy(), g[keys[0]])
+    assert len(keys) - 1 == len(m.record)
+    for k, (tag, t) in zip(keys[1:], m.record):
+        assert k.endswith(tag)
+        assert np.array_equal(t.numpy(), g[k]), k
+    assert np.array_equal(logits, g["logits"])
+    assert np.array_equal(logits.argmax(1), g["logits"].argmax(1))
+
+
+def test_alexnet_golden():
+    g = load_golden("net_alexnet")
+    m = build_module("alexnet", W.make_weights("alexnet", 0), qparams=_qp(g))
+    m.record = []
+    x = W.make_images("alexnet", 2, 2)
+    logits = m(i8ie.tensor(x)).numpy()
+    tags = [str(t) for t in g["op_tags"]]
+    assert tags[1:] == [t for t, _ in m.record]
+    for (tag, t), sha in zip(m.record, g["op_sha256"][1:]):
+        assert hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest() == str(sha), tag
+    assert np.array_equal(logits, g["logits"])
+
+
+@pytest.mark.parametrize("topo,batch", [("simple_conv", 100), ("fc_mnist", 100), ("mini_alex", 33)])
+def test_net_vs_oracle_batch(topo, batch):
+    """BASELINE configs 1-2 at their full batch: calibrate on the B200 path (min/max
+    calibrator), feed the same ranges to the oracle, compare bit-exactly."""
+    sd = W.make_weights(topo, 0)
+    m = build_module(topo, sd, calib=W.make_images(topo, 100, 1))
+    qp = {n: (np.float32(L.layer._scale), int(L.layer._zp)) for n, L in m.layers().items()}
+    pm = models.PortModel(topo, sd)
+    pm.convert(qp)
+    x = W.make_images(topo, batch, 2)
+    exp = pm.forward_int8(x)
+    got = m(i8ie.tensor(x)).numpy()
+    assert np.array_equal(got, exp)
+    # calibration parity: the oracle's min/max calibration over ITS fp32 forward agrees to
+    # fp32-GEMM tolerance (the fp32 side is tolerance-only; unittest/test_layers.py uses atol 0.1)
+    qp_o = pm.calibrate_minmax(W.make_images(topo, 100, 1))
+    for n in qp:
+        assert abs(float(qp[n][0]) - float(qp_o[n][0])) <= 1e-3 * float(qp_o[n][0]) + 1e-6
+        assert abs(qp[n][1] - qp_o[n][1]) <= 1
+
+
+def test_alexnet_batch_properties():
+    """Full-size AlexNet-224, batch 100 (BASELINE config 3): images are independent, so
+    (1) rows of a big batch equal the same images run in small batches (batch-split
+    invariance — what multi-GPU sharding relies on), (2) the first two rows equal the
+    golden logits of the compiled reference, (3) a permuted batch gives permuted logits."""
+    g = load_golden("net_alexnet")
+    m = build_module("alexnet", W.make_weights("alexnet", 0), qparams=_qp(g))
+    x = W.make_images("alexnet", 100, 2)
+    full = m(i8ie.tensor(x)).numpy()
+    assert np.array_equal(full[:2], m(i8ie.tensor(x[:2])).numpy())
+    x2 = W.make_images("alexnet", 2, 2)          # the golden batch (same seed => same first rows?)
+    if np.array_equal(x2, x[:2]):
+        assert np.array_equal(full[:2], g["logits"])
+    assert np.array_equal(m(i8ie.tensor(x2)).numpy(), g["logits"])
+    parts = np.concatenate([m(i8ie.tensor(x[i:i + 25])).numpy() for i in range(0, 100, 25)])
+    assert np.array_equal(full, parts)
+    perm = np.random.default_rng(0).permutation(100)
+    assert np.array_equal(m(i8ie.tensor(x[perm])).numpy(), full[perm])
