@@ -171,8 +171,9 @@ def test_zp_offsets(n, k, zp):
     qb = rng.integers(-128, 128, size=(n,), dtype=np.int8)
     oc = torch.empty(n, dtype=torch.int32, device="cuda")
     bf = torch.empty(n, dtype=torch.float32, device="cuda")
+    qw_d, qb_d = dev(qw), dev(qb)   # keep both alive: temporaries would alias in the caching allocator
     for is_conv in (1, 0):
-        _check(lib().i8ie_zp_offsets(dev(qw).data_ptr(), dev(qb).data_ptr(), n, k, zp, 0.025, is_conv,
+        _check(lib().i8ie_zp_offsets(qw_d.data_ptr(), qb_d.data_ptr(), n, k, zp, 0.025, is_conv,
                                      oc.data_ptr(), bf.data_ptr(), stream()))
         if is_conv:
             exp = port.conv_offsets(qw, qb, zp, np.float32(0.025))
