@@ -153,6 +153,11 @@ I8IE_API int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int
                int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
                float sc, int zp_out, int flags, int32_t* acc_out, int impl, void* stream);
 
+/* Debug hook (not part of the reference-facing surface): synchronises the device and
+ * returns the first protocol error (mbarrier wait timeout) a tensor-core kernel recorded
+ * (0 = none, >0 = role that timed out), optionally clearing it; negative on CUDA errors. */
+I8IE_API int i8ie_debug_tc_error(int reset);
+
 #ifdef __cplusplus
 }
 #endif

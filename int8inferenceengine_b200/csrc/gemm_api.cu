@@ -1,14 +1,64 @@
 // C-ABI entry points for the GEMM-shaped ops: conv2d plan/run and fully-connected.
+// Dispatch is by SHAPE only (alignment / size), never by backend: both kernels are sm_100a
+// CUDA; the tcgen05 kernel takes every shape whose K blocks are TMA/UMMA-aligned.
+#include <cstdlib>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "gemm_api.cuh"
 
 using namespace i8ie;
 
+namespace {
+
+struct MapCacheEntry {
+  const void* ptr;
+  long long a, b, c, d;
+  CUtensorMap map;
+};
+
+// small pointer-keyed cache: encoding a CUtensorMap costs microseconds on the host and the
+// activation buffers of a served model are recycled (CUDA-graph replays reuse them exactly)
+class MapCache {
+ public:
+  template <typename MakeFn>
+  int get(const void* ptr, long long a, long long b, long long c, long long d, CUtensorMap* out, MakeFn make) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& e : entries_)
+      if (e.ptr == ptr && e.a == a && e.b == b && e.c == c && e.d == d) { *out = e.map; return I8IE_OK; }
+    MapCacheEntry e{ptr, a, b, c, d, {}};
+    int rc = make(&e.map);
+    if (rc != I8IE_OK) return rc;
+    if (entries_.size() >= 256) entries_.erase(entries_.begin());
+    entries_.push_back(e);
+    *out = e.map;
+    return I8IE_OK;
+  }
+
+ private:
+  std::mutex mu_;
+  std::vector<MapCacheEntry> entries_;
+};
+
+MapCache g_fc_maps;
+
+bool tc_disabled() {
+  static const bool off = std::getenv("I8IE_DISABLE_TC") != nullptr;
+  return off;
+}
+
+}  // namespace
+
 struct i8ie_conv_plan {
   GemmGeom g;
   const int8_t* w_packed;
   int impl;  // 1 = SIMT dp4a, 2 = tcgen05
+  // tcgen05 state
+  int bk, bn;
+  CUtensorMap tmB;
+  int32_t* border_tab;  // device, owned
+  MapCache amaps;
 };
 
 extern "C" {
@@ -36,16 +86,45 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   g.M = n * g.oh * g.ow; g.N = kc; g.n_pad = kc_pad;
   g.ldw = kh * kw * cp; g.out_cp = out_cp;
   p->w_packed = w_packed;
-  if (impl == 2) {
-    set_error("conv2d_plan_create: tcgen05 path not available for this geometry");
+  p->border_tab = nullptr;
+  const bool eligible = tc_conv_eligible(g) && !tc_disabled();
+  if (impl == 2 && !eligible) {
+    set_error("conv2d_plan_create: geometry not eligible for the tcgen05 kernel (cp=%d must be a multiple of 32, pad<=3)", cp);
     delete p;
     return nullptr;
   }
-  p->impl = 1;
+  p->impl = (impl == 1 || !eligible) ? 1 : 2;
+  if (p->impl == 2) {
+    p->bk = tc_conv_bk(g);
+    p->bn = tc_pick_bn(g.N);
+    int rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->bn);
+    const int tab = tc_border_table_size(g);
+    if (rc == I8IE_OK && tab > 0) {
+      if (cudaMalloc(&p->border_tab, sizeof(int32_t) * (size_t)tab) != cudaSuccess) {
+        set_error("conv2d_plan_create: cudaMalloc of the border table failed");
+        rc = I8IE_ECUDA;
+      } else {
+        rc = tc_build_border_table(g, w_packed, p->border_tab, 0);
+        if (rc == I8IE_OK && cudaStreamSynchronize(0) != cudaSuccess) {
+          set_error("conv2d_plan_create: border table kernel failed");
+          rc = I8IE_ECUDA;
+        }
+      }
+    }
+    if (rc != I8IE_OK) {
+      if (p->border_tab) cudaFree(p->border_tab);
+      delete p;
+      return nullptr;
+    }
+  }
   return p;
 }
 
-void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan) { delete plan; }
+void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan) {
+  if (!plan) return;
+  if (plan->border_tab) cudaFree(plan->border_tab);
+  delete plan;
+}
 
 int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan) { return plan ? plan->impl : 0; }
 
@@ -54,6 +133,15 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   I8IE_REQUIRE(plan && x && y && oc, "conv2d_u8: null argument");
   I8IE_REQUIRE(zp_in >= 0 && zp_in <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_u8: zero point out of range");
   EpiParams ep{oc, nullptr, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  if (plan->impl == 2) {
+    CUtensorMap tmA;
+    int rc = plan->amaps.get(x, 0, 0, 0, 0, &tmA, [&](CUtensorMap* m) {
+      return tc_encode_act_map_im2col(m, x, plan->g, plan->bk);
+    });
+    if (rc != I8IE_OK) return rc;
+    return launch_tc_conv(plan->g, tmA, plan->tmB, plan->bk, plan->bn, plan->border_tab, y, ep, zp_in,
+                          (cudaStream_t)stream);
+  }
   return launch_simt_igemm(plan->g, x, plan->w_packed, y, ep, zp_in, (cudaStream_t)stream);
 }
 
@@ -65,13 +153,40 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
                    ldw >= ldx && ldy >= n && n_pad >= n,
                "fc_u8: bad shape/pitch (m=%d n=%d k=%d ldx=%d ldw=%d ldy=%d n_pad=%d)", m, n, k, ldx, ldw, ldy, n_pad);
   I8IE_REQUIRE(zp_out >= 0 && zp_out <= 255, "fc_u8: zero point out of range");
-  I8IE_REQUIRE(impl != 2, "fc_u8: tcgen05 path not available for this shape");
+  EpiParams ep{oc, bias_f, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  // shape dispatch: the tensor-core kernel needs at least one full 32-byte K step to be worthwhile
+  const bool eligible = !tc_disabled() && k >= 32;
+  I8IE_REQUIRE(!(impl == 2 && !eligible), "fc_u8: shape not eligible for the tcgen05 kernel");
+  if (impl != 1 && eligible) {
+    // one M tile: favour narrow N tiles so that enough CTAs stream the weights
+    int bn = tc_pick_bn(n);
+    if (m <= 128) bn = (n >= 2048) ? 32 : (n >= 512 ? 64 : bn);
+    else if (m <= 512 && bn > 128) bn = 128;
+    CUtensorMap tmA, tmB;
+    int rc = g_fc_maps.get(x, m, k, ldx, 1, &tmA, [&](CUtensorMap* mp) { return tc_encode_act_map_rows(mp, x, m, k, ldx); });
+    if (rc != I8IE_OK) return rc;
+    rc = g_fc_maps.get(w, n_pad, ldw, bn, 2, &tmB,
+                       [&](CUtensorMap* mp) { return tc_encode_weight_map(mp, w, n_pad, ldw, 128, bn); });
+    if (rc != I8IE_OK) return rc;
+    return launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, y, ep, (cudaStream_t)stream);
+  }
   GemmGeom g;
   g.n = m; g.h = 1; g.w = 1; g.cp = ldx;
   g.kh = 1; g.kw = 1; g.stride = 1; g.pad = 0;
   g.oh = 1; g.ow = 1; g.M = m; g.N = n; g.n_pad = n_pad; g.ldw = ldw; g.out_cp = ldy;
-  EpiParams ep{oc, bias_f, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
   return launch_simt_igemm(g, x, w, y, ep, 0, (cudaStream_t)stream);
+}
+
+// Debug hook: first protocol error (timeout) recorded by a tensor-core kernel, 0 if none.
+// Synchronises the device. Not part of the reference-facing surface.
+int i8ie_debug_tc_error(int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("debug_tc_error: %s", cudaGetErrorString(cudaGetLastError()));
+    return I8IE_ECUDA;
+  }
+  int v = 0;
+  int rc = tc_read_error(&v, reset != 0);
+  return rc != I8IE_OK ? rc : v;
 }
 
 }  // extern "C"

@@ -1,6 +1,8 @@
 // Internal interface between the C-ABI entry points (gemm_api.cu) and the
 // GEMM-shaped kernels (simt_gemm.cu, tc_gemm.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace i8ie {
@@ -19,5 +21,21 @@ struct GemmGeom {
 
 int launch_simt_igemm(const GemmGeom& g, const uint8_t* x, const int8_t* w, uint8_t* y,
                       const EpiParams& ep, int zp_in, cudaStream_t stream);
+
+
+// ---- tcgen05 path (tc_gemm.cu) ---------------------------------------------------------
+bool tc_conv_eligible(const GemmGeom& g);
+int tc_conv_bk(const GemmGeom& g);
+int tc_pick_bn(int n);
+int tc_border_table_size(const GemmGeom& g);   // entries (int32) of the zero-point border table
+int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* tab, cudaStream_t stream);
+int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn);
+int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int bk);
+int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx);
+int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn,
+                   const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream);
+int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
+                 const EpiParams& ep, cudaStream_t stream);
+int tc_read_error(int* out, bool reset);
 
 }  // namespace i8ie

@@ -1,0 +1,419 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernel for the i8ie INT8 path.
+//
+//   D[M, N] (s32, TMEM) = A[M, K] (u8) * W[N, K]^T (s8),  K-major operands in shared memory
+//
+// conv2d (conv2d.cc:100-142): A is never materialised. The TMA engine gathers it straight
+//   from the NHWC activation tensor in IM2COL mode — one box = 128 consecutive output pixels
+//   (walking W, then H, then N exactly like the reference's row index ti*ow+tj) x BK channels
+//   of one filter tap — and zero-fills spatially out-of-range taps. The reference pads with
+//   the input zero_point instead (conv2d.cc:24-25); the exact integer difference
+//   zp * sum_{out-of-range taps} w is added back in the epilogue from a per-border-class
+//   table, so the s32 accumulators are bit-identical.
+// fully_connected (fully_connected.cc:22-52): A is a plain 2-D TMA tile of the [M, K] rows.
+//
+// Warp-specialised, one 128 x BN output tile per CTA:
+//   warp 0     TMA producer (one elected lane), STAGES-deep mbarrier ring
+//   warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma kind::i8, M=128, N=BN, K=32
+//   warps 2-5  epilogue: tcgen05.ld -> + oc (+ border correction) [-> fc float bias] -> requantise
+//              (the reference's exact fp32 sequence) -> [relu] -> packed u8 NHWC store
+// Several CTAs are co-resident per SM (TMEM: BN columns each), so one CTA's epilogue
+// overlaps another's main loop.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_api.cuh"
+#include "tc_ptx.cuh"
+
+namespace i8ie {
+
+__device__ int g_tc_error = 0;  // first protocol error seen by any tensor-core kernel (0 = none)
+
+struct TcParams {
+  int M, N, out_cp;
+  int num_kb;      // K blocks of BK bytes
+  int cblocks;     // K blocks per filter tap (im2col)
+  int kh, kw, stride, pad, H, W, oh, ow;
+  int zp_in;
+  const int32_t* border_tab;  // [(pad+1)^4][N] or nullptr
+  uint8_t* y;
+  EpiParams ep;
+};
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int kThreads = 192;
+
+template <int BN>
+constexpr uint32_t tmem_cols() {
+  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+}
+
+template <int BN, int BK, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK;
+  static constexpr int kBBytes = BN * BK;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTileBytes = STAGES * kStageBytes;
+  // after the tiles: full[STAGES], empty[STAGES], tmem_full, tmem slot, oc[BN], bias[BN]
+  static constexpr int kBarOff = kTileBytes;
+  static constexpr int kOcOff = kBarOff + (2 * STAGES + 1) * 8 + 8;
+  static constexpr int kBiasOff = kOcOff + BN * 4;
+  static constexpr int kTotal = kBiasOff + BN * 4;
+  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-byte alignment
+};
+
+template <int BN, int BK, int STAGES, bool IM2COL>
+__global__ void __launch_bounds__(kThreads) tc_igemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const TcParams p) {
+  using L = SmemLayout<BN, BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  int32_t* s_oc = reinterpret_cast<int32_t*>(smem + L::kOcOff);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, tmem_cols<BN>());
+  if (warp >= 2) {
+    for (int j = threadIdx.x - 64; j < BN; j += kThreads - 64) {
+      const int n = n0 + j;
+      s_oc[j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
+      s_bias[j] = (n < p.N && p.ep.bias_f) ? __ldg(p.ep.bias_f + n) : 0.f;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int bw = 0, bh = 0, bn = 0;
+      if (IM2COL) {
+        const int q = m0 % p.ow, t = m0 / p.ow;
+        bw = q * p.stride - p.pad;
+        bh = (t % p.oh) * p.stride - p.pad;
+        bn = t / p.oh;
+      }
+      int cb = 0, kx = 0, ky = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        if (!ptx::mbar_wait(&empty_bar[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); break; }
+        ptx::mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        if (IM2COL) {
+          ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[s], cb * BK, bw, bh, bn, (uint16_t)kx, (uint16_t)ky);
+          if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
+        } else {
+          ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+        }
+        ptx::tma_load_2d(sa + L::kABytes, &tmB, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
+      bool ok = true;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        if (!ptx::mbar_wait(&full_bar[s], ph)) { atomicCAS(&g_tc_error, 0, 2); ok = false; break; }
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 32; ++k) {
+          ptx::mma_i8_ss(tmem_base, ptx::make_smem_desc<BK>(sa + k * 32), ptx::make_smem_desc<BK>(sb + k * 32),
+                         idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+      }
+      if (ok) ptx::tc_commit(tmem_full_bar);
+      else ptx::mbar_arrive(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue (4 warps; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)) =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    const bool ok = ptx::mbar_wait(tmem_full_bar, 0);
+    if (!ok) atomicCAS(&g_tc_error, 0, 3);
+    ptx::tc_fence_after();
+    // spatial border class of this output pixel -> row of the zero-point correction table
+    const int32_t* corr = nullptr;
+    if (IM2COL && p.border_tab && m < p.M) {
+      const int q = m % p.ow, pr = (m / p.ow) % p.oh;
+      const int y0 = pr * p.stride - p.pad, x0 = q * p.stride - p.pad;
+      const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
+      const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
+      const int d = p.pad + 1;
+      const int cls = ((th * d + bh) * d + tw) * d + bw;
+      if (cls != 0) corr = p.border_tab + (size_t)cls * p.N;
+    }
+    const float zpf = (float)p.ep.zp_out;
+    const uint32_t zpo = (uint32_t)p.ep.zp_out;
+    uint8_t* yrow = p.y + (size_t)m * p.out_cp;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.out_cp) break;  // warp-uniform
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      ptx::tmem_ld_wait();
+      uint32_t packed[8];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + c0 + j;
+        uint32_t qv = zpo;  // pad lanes carry the zero point
+        if (n < p.N) {
+          int32_t a = (int32_t)v[j] + s_oc[c0 + j];
+          if (corr) a += p.zp_in * __ldg(corr + n);
+          if (p.ep.bias_f) a = fc_bias_add(a, s_bias[c0 + j]);
+          if (p.ep.acc_out && m < p.M) p.ep.acc_out[(size_t)m * p.N + n] = a;
+          qv = requant_u8(a, p.ep.sa, p.ep.sb, p.ep.sc, zpf);
+          if (p.ep.relu) qv = max(qv, zpo);
+        }
+        if ((j & 3) == 0) packed[j >> 2] = qv;
+        else packed[j >> 2] |= qv << (8 * (j & 3));
+      }
+      if (m < p.M && ok) {
+        if (n0 + c0 < p.out_cp)
+          *reinterpret_cast<uint4*>(yrow + n0 + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        if (n0 + c0 + 16 < p.out_cp)
+          *reinterpret_cast<uint4*>(yrow + n0 + c0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
+}
+
+// zero-point border correction table: tab[cls][n] = sum over spatially out-of-range taps of
+// the packed weight, cls = ((th*(pad+1)+bh)*(pad+1)+tw)*(pad+1)+bw  (rows [0,th) and
+// [kh-bh,kh), cols [0,tw) and [kw-bw,kw) are out of range).
+__global__ void border_table_kernel(const int8_t* __restrict__ wp, int32_t* __restrict__ tab, int N, int kh,
+                                    int kw, int cp, int pad) {
+  const int d = pad + 1;
+  const int ncls = d * d * d * d;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ncls * N) return;
+  const int n = idx % N, cls = idx / N;
+  const int bw = cls % d, tw = (cls / d) % d, bh = (cls / (d * d)) % d, th = cls / (d * d * d);
+  int32_t s = 0;
+  for (int r = 0; r < kh; ++r)
+    for (int c = 0; c < kw; ++c) {
+      const bool inb = (r >= th) && (r < kh - bh) && (c >= tw) && (c < kw - bw);
+      if (inb) continue;
+      const int8_t* w = wp + (((size_t)n * kh + r) * kw + c) * cp;
+      for (int ch = 0; ch < cp; ++ch) s += w[ch];
+    }
+  tab[idx] = s;
+}
+
+// ---- host side: tensor maps -------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename Fn>
+Fn driver_fn(const char* name) {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<Fn>(f);
+}
+
+CUtensorMapSwizzle swizzle_for(int bk) {
+  return bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+int encode_tiled_2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch, int box_cols,
+                    int box_rows) {
+  static EncodeTiledFn fn = driver_fn<EncodeTiledFn>("cuTensorMapEncodeTiled");
+  I8IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  I8IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu pitch=%llu box=%dx%d",
+               (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch, box_cols, box_rows);
+  return I8IE_OK;
+}
+
+int encode_im2col_4d(CUtensorMap* tm, const void* base, const GemmGeom& g, int bk) {
+  static EncodeIm2colFn fn = driver_fn<EncodeIm2colFn>("cuTensorMapEncodeIm2col");
+  I8IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)g.cp, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
+  cuuint64_t strides[3] = {(cuuint64_t)g.cp, (cuuint64_t)g.cp * g.w, (cuuint64_t)g.cp * g.w * g.h};
+  // bounding box of the filter's top-left tap, (W, H) order: [-pad, dim - 1 + pad - (k - 1)]
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.kw - 1), g.pad - (g.kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                  (cuuint32_t)bk, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  I8IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d): c=%d w=%d h=%d n=%d k=%dx%d s=%d p=%d bk=%d",
+               (int)r, g.cp, g.w, g.h, g.n, g.kh, g.kw, g.stride, g.pad, bk);
+  return I8IE_OK;
+}
+
+template <int BN, int BK, int STAGES, bool IM2COL>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN, BK, STAGES>;
+  static bool attr_set = false;
+  auto kern = tc_igemm_kernel<BN, BK, STAGES, IM2COL>;
+  if (!attr_set) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    attr_set = true;
+  }
+  dim3 grid((p.M + BM - 1) / BM, (p.out_cp + BN - 1) / BN);
+  kern<<<grid, kThreads, L::kDynamic, stream>>>(tmA, tmB, p);
+  return check_launch("tc_igemm_kernel");
+}
+
+// stage counts: keep >= 2 CTAs per SM resident (epilogue/main-loop overlap) where smem allows
+template <int BK, bool IM2COL>
+int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+  switch (bn) {
+    case 32:  return launch_cfg<32, BK, (BK == 128 ? 4 : 6), IM2COL>(tmA, tmB, p, stream);
+    case 64:  return launch_cfg<64, BK, (BK == 128 ? 4 : 6), IM2COL>(tmA, tmB, p, stream);
+    case 128: return launch_cfg<128, BK, (BK == 128 ? 3 : BK == 64 ? 6 : 8), IM2COL>(tmA, tmB, p, stream);
+    case 192: return launch_cfg<192, BK, (BK == 128 ? 2 : BK == 64 ? 5 : 8), IM2COL>(tmA, tmB, p, stream);
+    case 256: return launch_cfg<256, BK, (BK == 128 ? 2 : BK == 64 ? 4 : 8), IM2COL>(tmA, tmB, p, stream);
+  }
+  set_error("tcgen05: unsupported BN %d", bn);
+  return I8IE_EINVAL;
+}
+
+template <bool IM2COL>
+int launch_bk(int bk, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+  if (bk == 128) return launch_bn<128, IM2COL>(bn, tmA, tmB, p, stream);
+  if constexpr (IM2COL) {  // the row-tiled (fc) operand always uses 128-byte K blocks
+    if (bk == 64) return launch_bn<64, IM2COL>(bn, tmA, tmB, p, stream);
+    if (bk == 32) return launch_bn<32, IM2COL>(bn, tmA, tmB, p, stream);
+  }
+  set_error("tcgen05: unsupported BK %d", bk);
+  return I8IE_EINVAL;
+}
+
+int pick_bn(int n) {
+  if (const char* e = std::getenv("I8IE_TC_BN")) {
+    const int v = std::atoi(e);
+    if (v == 32 || v == 64 || v == 128 || v == 192 || v == 256) return v;
+  }
+  if (n <= 32) return 32;
+  if (n <= 64) return 64;
+  if (n <= 128) return 128;
+  if (n <= 192) return 192;
+  if (n <= 256) return 256;
+  // fewest padded columns; ties -> larger tile
+  int best = 256, best_waste = 1 << 30;
+  for (int bn : {256, 192, 128}) {
+    const int waste = (n + bn - 1) / bn * bn - n;
+    if (waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  return best;
+}
+
+}  // namespace
+
+// ---- entry points used by gemm_api.cu --------------------------------------------------------
+
+bool tc_conv_eligible(const GemmGeom& g) {
+  // K blocks are whole 32-byte multiples of one tap's channel run; corner offsets fit TMA's s8 range
+  return g.cp % 32 == 0 && g.pad <= 3 && g.stride <= 8 && g.kh <= 128 && g.kw <= 128 && g.out_cp % 16 == 0;
+}
+
+int tc_conv_bk(const GemmGeom& g) { return g.cp % 128 == 0 ? 128 : g.cp % 64 == 0 ? 64 : 32; }
+
+int tc_border_table_size(const GemmGeom& g) {
+  if (g.pad == 0) return 0;
+  const int d = g.pad + 1;
+  return d * d * d * d * g.N;
+}
+
+int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* tab, cudaStream_t stream) {
+  const int total = tc_border_table_size(g);
+  if (total == 0) return I8IE_OK;
+  border_table_kernel<<<(total + 127) / 128, 128, 0, stream>>>(w_packed, tab, g.N, g.kh, g.kw, g.cp, g.pad);
+  return check_launch("border_table_kernel");
+}
+
+int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn) {
+  return encode_tiled_2d(tm, w, (uint64_t)ldw, (uint64_t)rows, (uint64_t)ldw, bk, bn);
+}
+
+int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int bk) {
+  return encode_im2col_4d(tm, x, g, bk);
+}
+
+int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx) {
+  return encode_tiled_2d(tm, x, (uint64_t)k, (uint64_t)m, (uint64_t)ldx, 128, BM);
+}
+
+int tc_pick_bn(int n) { return pick_bn(n); }
+
+int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn,
+                   const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream) {
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
+  p.cblocks = g.cp / bk;
+  p.num_kb = g.kh * g.kw * p.cblocks;
+  p.kh = g.kh; p.kw = g.kw; p.stride = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
+  p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
+  return launch_bk<true>(bk, bn, tmA, tmB, p, stream);
+}
+
+int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
+                 const EpiParams& ep, cudaStream_t stream) {
+  TcParams p;
+  p.M = m; p.N = n; p.out_cp = ldy;
+  p.cblocks = 1; p.num_kb = (k + 127) / 128;
+  p.kh = p.kw = 1; p.stride = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
+  p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
+  return launch_bk<false>(128, bn, tmA, tmB, p, stream);
+}
+
+int tc_read_error(int* out, bool reset) {
+  int v = 0;
+  I8IE_CUDA_OK(cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int)));
+  if (reset && v != 0) {
+    const int z = 0;
+    I8IE_CUDA_OK(cudaMemcpyToSymbol(g_tc_error, &z, sizeof(int)));
+  }
+  *out = v;
+  return I8IE_OK;
+}
+
+}  // namespace i8ie

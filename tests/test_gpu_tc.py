@@ -1,0 +1,88 @@
+"""-m gpu: the tcgen05 (kind::i8) kernels specifically — forced impl=2 — against the oracle:
+s32 accumulators and u8 outputs bit-exact, no protocol timeouts, on TMA-aligned shapes
+incl. ragged M / N / K tails, zero-point border correction, stride, and every K-block width."""
+import numpy as np
+import pytest
+import torch
+
+from int8inferenceengine_b200 import _lib
+from oracle import port
+
+from gpu_utils import make_layer, u8_tensor_from_nchw
+
+pytestmark = pytest.mark.gpu
+
+
+def _no_tc_error():
+    assert _lib.load().i8ie_debug_tc_error(1) == 0, "a tensor-core kernel hit a barrier timeout"
+
+
+FC = [(128, 32, 32), (128, 128, 32), (1, 64, 16), (100, 784, 10), (100, 7680, 10), (128, 9216, 256),
+      (300, 1000, 200), (130, 4096, 4096), (1000, 4096, 10), (257, 515, 129), (17, 33, 700)]
+
+
+@pytest.mark.parametrize("shape", FC)
+def test_tc_fc(shape):
+    m, k, n = shape
+    rng = np.random.default_rng(m * 7 + k + n)
+    a = np.sqrt(6.0 / k)
+    w = rng.uniform(-a, a, size=(n, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(n,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(m, k), dtype=np.uint8)
+    in_scale, in_zp, out_scale, out_zp = np.float32(0.0518), 116, np.float32(0.18), 127
+    L = make_layer("fc", w, b, (out_scale, out_zp))
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.linear_u8(q, qw, qb, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    acc = torch.empty(m * n, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    _no_tc_error()
+    assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    # pad lanes of the padded output rows carry the zero point
+    ldy = (n + 15) // 16 * 16
+    raw = out.buf.cpu().numpy().reshape(m, ldy)
+    assert np.all(raw[:, n:] == out_zp)
+
+
+CONV = [  # n, c, h, w, kc, k, stride, pad
+    (2, 32, 8, 8, 32, 1, 1, 0), (2, 32, 8, 8, 32, 3, 1, 0), (2, 32, 8, 8, 32, 3, 1, 1),
+    (3, 64, 13, 13, 96, 3, 1, 1), (2, 96, 27, 27, 256, 5, 1, 2), (2, 256, 13, 13, 384, 3, 1, 1),
+    (2, 384, 13, 13, 256, 3, 1, 1), (2, 128, 9, 11, 64, 3, 2, 1), (1, 32, 20, 20, 40, 5, 3, 2),
+    (5, 50, 12, 12, 120, 5, 1, 0), (4, 20, 28, 28, 50, 5, 1, 0), (1, 160, 5, 5, 10, 5, 1, 2),
+    (7, 64, 6, 6, 300, 3, 1, 3),
+]
+
+
+@pytest.mark.parametrize("geom", CONV)
+def test_tc_conv(geom):
+    n, c, h, w_, kc, k, s, p = geom
+    rng = np.random.default_rng(sum(geom))
+    a = np.sqrt(6.0 / (c * k * k))
+    w = rng.uniform(-a, a, size=(kc, c, k, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(kc,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(n, c, h, w_), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0293), int(rng.integers(1, 256))
+    out_scale, out_zp = np.float32(0.061), int(rng.integers(60, 190))
+    L = make_layer("conv", w, b, (out_scale, out_zp), s, p)
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.conv2d_u8(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    oh, ow = exp.shape[2], exp.shape[3]
+    acc = torch.empty(n * oh * ow * kc, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    _no_tc_error()
+    assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    L.fuse_relu = True
+    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=2)
+    assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
+
+
+def test_tc_ineligible_shapes_are_refused_when_forced():
+    rng = np.random.default_rng(0)
+    w = rng.uniform(-0.3, 0.3, size=(8, 3, 3, 3)).astype(np.float32)   # cp = 16: not a 32-byte K block
+    L = make_layer("conv", w, np.zeros(8, np.float32), (np.float32(0.05), 128), 1, 1)
+    q = rng.integers(0, 256, size=(1, 3, 8, 8), dtype=np.uint8)
+    with pytest.raises(RuntimeError):
+        L._forward_u8(u8_tensor_from_nchw(q, 0.03, 77), impl=2)
+    # ... and taken by the SIMT kernel under auto dispatch
+    L._forward_u8(u8_tensor_from_nchw(q, 0.03, 77), impl=0)
