@@ -135,7 +135,8 @@ I8IE_API i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int
                                         int stride, int pad, int out_cp, const int8_t* w_packed,
                                         int kc_pad, int impl);
 I8IE_API void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan);
-/* Which kernel the plan resolved to: 1 = SIMT dp4a, 2 = tcgen05. */
+/* Which kernel the plan resolved to: 1 = SIMT dp4a, 2 = tcgen05 (TMA im2col), 3 = tcgen05 stem
+ * (small-C strided first layer: the plan owns a bordered superpixel copy of the input). */
 I8IE_API int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan);
 /* y = requant(conv(x) + oc) [+relu]; sa=in.scale, sb=weight scale, sc=layer scale_,
  * zp_in = in.zero_point (spatial padding value, conv2d.cc:129-130), zp_out = layer
@@ -144,6 +145,14 @@ I8IE_API int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan);
 I8IE_API int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int32_t* oc,
                    float sa, float sb, float sc, int zp_in, int zp_out, int flags,
                    int32_t* acc_out, void* stream);
+
+/* Module.__call__'s input quantise (i8ie/module.py:20 -> quantize_utils.cc:44-52) fused into
+ * the first convolution: x is the fp32 NCHW image; q = (u8)(x/in_scale + in_zp) is produced
+ * on the fly into the plan's stem buffer and never stored as an NHWC tensor. Only valid
+ * for plans with impl 3; returns I8IE_EINVAL otherwise (quantise + i8ie_conv2d_u8 then). */
+I8IE_API int i8ie_conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, float in_scale, int in_zp, uint8_t* y,
+                       const int32_t* oc, float sb, float sc, int zp_out, int flags, int32_t* acc_out,
+                       void* stream);
 
 /* Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52:
  *   acc = x[m,k] * w[n,k]^T + oc[n];  acc = (int)((float)acc + bias_f[n]);  y = requant(acc) [+relu]

@@ -16,7 +16,7 @@ SYMBOLS = [
     "i8ie_minmax_f32", "i8ie_range_from_minmax_host", "i8ie_relu_u8", "i8ie_maxpool_u8_nhwc",
     "i8ie_u8_nchw_to_nhwc", "i8ie_u8_nhwc_to_nchw", "i8ie_quantize_weight_host", "i8ie_zp_offsets",
     "i8ie_pack_conv_weight", "i8ie_conv2d_plan_create", "i8ie_conv2d_plan_destroy",
-    "i8ie_conv2d_plan_impl", "i8ie_conv2d_u8", "i8ie_fc_u8", "i8ie_debug_tc_error",
+    "i8ie_conv2d_plan_impl", "i8ie_conv2d_u8", "i8ie_conv2d_f32_u8", "i8ie_fc_u8", "i8ie_debug_tc_error",
 ]
 
 _lib = None
@@ -66,6 +66,7 @@ def load():
     L.i8ie_conv2d_plan_impl.argtypes = [vp]
     L.i8ie_conv2d_u8.argtypes = [vp, vp, vp, vp, f, f, f, i, i, i, vp, vp]
     L.i8ie_fc_u8.argtypes = [vp, i, vp, i, i, vp, i, i, i, i, vp, vp, f, f, f, i, i, vp, i, vp]
+    L.i8ie_conv2d_f32_u8.argtypes = [vp, vp, f, i, vp, vp, f, f, i, i, vp, vp]
     L.i8ie_debug_tc_error.argtypes = [i]
     _lib = L
     return L

@@ -598,8 +598,37 @@ class Conv2d(_BaseLayer):
         out_cp = _r16(kc)
         out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=buf.device)
         plan = self._plan(n, c, h, w, cp, impl)
+        self._last_impl = int(L.i8ie_conv2d_plan_impl(plan))   # 1 SIMT, 2 tcgen05 im2col, 3 tcgen05 stem
         flags = 1 if self.fuse_relu else 0
         check(L.i8ie_conv2d_u8(plan, buf.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
                                float(self._w_scale), float(self._scale), x._zp, self._zp, flags,
                                acc_out.data_ptr() if acc_out is not None else None, _stream()), "conv2d_u8")
+        return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
+
+    def forward_quantize_fused(self, x, in_scale, in_zp, acc_out=None):
+        """Module.__call__'s input quantise (module.py:20) fused into this convolution
+        (i8ie_conv2d_f32_u8). Only stem-eligible layers (C <= 4, stride 4/8) support it;
+        returns None otherwise so the caller falls back to quantize() + __call__()."""
+        L = _lib.load()
+        if not self._is_quantized or not isinstance(x, TensorF32) or len(x._shape) != 4:
+            return None
+        n, c, h, w = x._shape
+        kc, cw, kh, kw = self._qw_shape
+        if c != cw or c > 4 or self._stride not in (4, 8):
+            return None
+        plan = self._plan(n, c, h, w, _r16(c), 0)
+        if int(L.i8ie_conv2d_plan_impl(plan)) != 3:
+            return None
+        in_scale = float(np.float32(in_scale))
+        oh = (h - kh + 2 * self._pad) // self._stride + 1
+        ow = (w - kw + 2 * self._pad) // self._stride + 1
+        oc, _ = self._offsets(int(in_zp), in_scale, True)
+        out_cp = _r16(kc)
+        out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=x.buf.device)
+        flags = 1 if self.fuse_relu else 0
+        check(L.i8ie_conv2d_f32_u8(plan, x.buf.data_ptr(), in_scale, int(in_zp), out.data_ptr(), oc.data_ptr(),
+                                   float(self._w_scale), float(self._scale), self._zp, flags,
+                                   acc_out.data_ptr() if acc_out is not None else None, _stream()),
+              "conv2d_f32_u8")
+        self._last_impl = 3
         return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)

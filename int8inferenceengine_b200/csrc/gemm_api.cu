@@ -53,13 +53,27 @@ bool tc_disabled() {
 struct i8ie_conv_plan {
   GemmGeom g;
   const int8_t* w_packed;
-  int impl;  // 1 = SIMT dp4a, 2 = tcgen05
+  int impl;  // 1 = SIMT dp4a, 2 = tcgen05 im2col, 3 = tcgen05 stem (small-C strided first layer)
+  int c;     // real input channels
   // tcgen05 state
   int bk, bn;
   CUtensorMap tmB;
   int32_t* border_tab;  // device, owned
   MapCache amaps;
+  // stem state (all device buffers owned by the plan)
+  StemGeom stem;
+  uint8_t* stem_x;      // bordered superpixel image, rewritten by every call
+  int8_t* stem_w;       // [kc_pad][kh][64]
+  CUtensorMap tmA_stem;
 };
+
+static void plan_free(i8ie_conv_plan* p) {
+  if (!p) return;
+  if (p->border_tab) cudaFree(p->border_tab);
+  if (p->stem_x) cudaFree(p->stem_x);
+  if (p->stem_w) cudaFree(p->stem_w);
+  delete p;
+}
 
 extern "C" {
 
@@ -87,17 +101,47 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   g.ldw = kh * kw * cp; g.out_cp = out_cp;
   p->w_packed = w_packed;
   p->border_tab = nullptr;
+  p->stem_x = nullptr;
+  p->stem_w = nullptr;
+  p->c = c;
+  const bool stem_ok = tc_stem_eligible(g, c) && !tc_disabled();
   const bool eligible = tc_conv_eligible(g) && !tc_disabled();
-  if (impl == 2 && !eligible) {
-    set_error("conv2d_plan_create: geometry not eligible for the tcgen05 kernel (cp=%d must be a multiple of 32, pad<=3)", cp);
-    delete p;
+  if (impl == 2 && !eligible && !stem_ok) {
+    set_error("conv2d_plan_create: geometry not eligible for a tcgen05 kernel (needs cp %% 32 == 0 and pad <= 3, "
+              "or c <= 4 with stride 4/8); cp=%d c=%d stride=%d", cp, c, stride);
+    plan_free(p);
     return nullptr;
   }
-  p->impl = (impl == 1 || !eligible) ? 1 : 2;
-  if (p->impl == 2) {
+  p->impl = (impl == 1 || (!eligible && !stem_ok)) ? 1 : (stem_ok ? 3 : 2);
+  int rc = I8IE_OK;
+  if (p->impl == 3) {
+    p->stem = tc_stem_geom(g, c);
+    p->bk = 64;
+    p->bn = tc_pick_bn(g.N);
+    if (cudaMalloc(&p->stem_x, (size_t)p->stem.bytes) != cudaSuccess ||
+        cudaMalloc(&p->stem_w, (size_t)kc_pad * kh * 64) != cudaSuccess) {
+      set_error("conv2d_plan_create: cudaMalloc of the stem buffers failed");
+      rc = I8IE_ECUDA;
+    }
+    if (rc == I8IE_OK) rc = tc_stem_pack_weights(g, c, w_packed, p->stem_w, 0);
+    if (rc == I8IE_OK && cudaStreamSynchronize(0) != cudaSuccess) {
+      set_error("conv2d_plan_create: stem weight kernel failed");
+      rc = I8IE_ECUDA;
+    }
+    if (rc == I8IE_OK) rc = tc_encode_weight_map(&p->tmB, p->stem_w, kc_pad, kh * 64, 64, p->bn);
+    if (rc == I8IE_OK) rc = tc_encode_stem_act_map(&p->tmA_stem, p->stem_x, g, p->stem);
+    if (rc != I8IE_OK && impl != 2) {
+      // the overlapping-window tensor map was refused: serve the layer with the SIMT kernel
+      cudaFree(p->stem_x); cudaFree(p->stem_w);
+      p->stem_x = nullptr; p->stem_w = nullptr;
+      p->impl = eligible ? 2 : 1;
+      rc = I8IE_OK;
+    }
+  }
+  if (rc == I8IE_OK && p->impl == 2) {
     p->bk = tc_conv_bk(g);
     p->bn = tc_pick_bn(g.N);
-    int rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->bn);
+    rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->bn);
     const int tab = tc_border_table_size(g);
     if (rc == I8IE_OK && tab > 0) {
       if (cudaMalloc(&p->border_tab, sizeof(int32_t) * (size_t)tab) != cudaSuccess) {
@@ -111,20 +155,15 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
         }
       }
     }
-    if (rc != I8IE_OK) {
-      if (p->border_tab) cudaFree(p->border_tab);
-      delete p;
-      return nullptr;
-    }
+  }
+  if (rc != I8IE_OK) {
+    plan_free(p);
+    return nullptr;
   }
   return p;
 }
 
-void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan) {
-  if (!plan) return;
-  if (plan->border_tab) cudaFree(plan->border_tab);
-  delete plan;
-}
+void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan) { plan_free(plan); }
 
 int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan) { return plan ? plan->impl : 0; }
 
@@ -133,6 +172,11 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   I8IE_REQUIRE(plan && x && y && oc, "conv2d_u8: null argument");
   I8IE_REQUIRE(zp_in >= 0 && zp_in <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_u8: zero point out of range");
   EpiParams ep{oc, nullptr, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  if (plan->impl == 3) {
+    int rc = tc_stem_pack_input(plan->g, plan->stem, x, plan->stem_x, zp_in, (cudaStream_t)stream);
+    if (rc != I8IE_OK) return rc;
+    return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+  }
   if (plan->impl == 2) {
     CUtensorMap tmA;
     int rc = plan->amaps.get(x, 0, 0, 0, 0, &tmA, [&](CUtensorMap* m) {
@@ -143,6 +187,18 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
                           (cudaStream_t)stream);
   }
   return launch_simt_igemm(plan->g, x, plan->w_packed, y, ep, zp_in, (cudaStream_t)stream);
+}
+
+int i8ie_conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, float in_scale, int in_zp, uint8_t* y,
+                       const int32_t* oc, float sb, float sc, int zp_out, int flags, int32_t* acc_out,
+                       void* stream) {
+  I8IE_REQUIRE(plan && x_nchw && y && oc, "conv2d_f32_u8: null argument");
+  I8IE_REQUIRE(plan->impl == 3, "conv2d_f32_u8: only stem plans fuse the input quantise (plan impl=%d)", plan->impl);
+  I8IE_REQUIRE(in_zp >= 0 && in_zp <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_f32_u8: zero point out of range");
+  EpiParams ep{oc, nullptr, in_scale, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  int rc = tc_stem_quantize_input(plan->g, plan->stem, x_nchw, plan->stem_x, in_scale, in_zp, (cudaStream_t)stream);
+  if (rc != I8IE_OK) return rc;
+  return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
 }
 
 int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,

@@ -38,4 +38,20 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
                  const EpiParams& ep, cudaStream_t stream);
 int tc_read_error(int* out, bool reset);
 
+// stem path (small-C strided first-layer convs), see tc_gemm.cu
+struct StemGeom {
+  int c;          // real input channels (<= 4)
+  int hp, wsp;    // rows / 16-byte superpixels per row of the bordered stem image
+  int64_t bytes;  // size of the stem buffer for the plan's batch
+};
+bool tc_stem_eligible(const GemmGeom& g, int c);
+StemGeom tc_stem_geom(const GemmGeom& g, int c);
+int tc_stem_pack_weights(const GemmGeom& g, int c, const int8_t* w_packed, int8_t* ws, cudaStream_t stream);
+int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, uint8_t* xs, int zp, cudaStream_t stream);
+int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, uint8_t* xs, float scale, int zp,
+                           cudaStream_t stream);
+int tc_encode_stem_act_map(CUtensorMap* tm, const uint8_t* xs, const GemmGeom& g, const StemGeom& s);
+int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
+                   const EpiParams& ep, cudaStream_t stream);
+
 }  // namespace i8ie

@@ -35,7 +35,7 @@ struct TcParams {
   int M, N, out_cp;
   int num_kb;      // K blocks of BK bytes
   int cblocks;     // K blocks per filter tap (im2col)
-  int kh, kw, stride, pad, H, W, oh, ow;
+  int kh, kw, stride_h, stride_w, pad, H, W, oh, ow;
   int zp_in;
   const int32_t* border_tab;  // [(pad+1)^4][N] or nullptr
   uint8_t* y;
@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(kThreads) tc_igemm_kernel(const __grid_constan
       int bw = 0, bh = 0, bn = 0;
       if (IM2COL) {
         const int q = m0 % p.ow, t = m0 / p.ow;
-        bw = q * p.stride - p.pad;
-        bh = (t % p.oh) * p.stride - p.pad;
+        bw = q * p.stride_w - p.pad;
+        bh = (t % p.oh) * p.stride_h - p.pad;
         bn = t / p.oh;
       }
       int cb = 0, kx = 0, ky = 0;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) tc_igemm_kernel(const __grid_constan
     const int32_t* corr = nullptr;
     if (IM2COL && p.border_tab && m < p.M) {
       const int q = m % p.ow, pr = (m / p.ow) % p.oh;
-      const int y0 = pr * p.stride - p.pad, x0 = q * p.stride - p.pad;
+      const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
       const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
       const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
       const int d = p.pad + 1;
@@ -231,6 +231,83 @@ __global__ void border_table_kernel(const int8_t* __restrict__ wp, int32_t* __re
       for (int ch = 0; ch < cp; ++ch) s += w[ch];
     }
   tab[idx] = s;
+}
+
+
+// ---- stem path: small-C strided first-layer convs (AlexNet conv1: C=3, k=11, s=4, p=2) ------
+// A 3-channel NHWC image gives TMA/UMMA nothing to chew on (K blocks must be >= 32 bytes).
+// The stem layout packs 4 pixels x 4 channel lanes into one 16-byte "superpixel" and bakes the
+// spatial zero-point border in physically (the window start 4*ox - pad must land on a
+// superpixel boundary, so the image is stored shifted by `pad`):
+//     xs[n][y][wsp][16],  y in [0, hp), hp = (oh-1)*s + kh,  wsp = (ow-1)*s/4 + 4
+//     pixel (y, x) of the bordered image lives at superpixel x/4, lanes 4*(x%4) + ch
+// One filter row of an output pixel is then ONE contiguous 64-byte run (16 px x 4 lanes, the
+// first kw px used), fetched by an im2col tensor map whose W stride is 16 bytes (windows
+// overlap). GEMM K = kh * 64.
+__global__ void stem_pack_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ xs, int n, int c, int h,
+                                 int w, int cp, int pad, int hp, int wsp, uint32_t zp) {
+  const int64_t total = (int64_t)n * hp * wsp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int sx = (int)(t % wsp);
+    const int y = (int)((t / wsp) % hp);
+    const int img = (int)(t / ((int64_t)wsp * hp));
+    const int row = y - pad;
+    const uint32_t zp4 = zp * 0x01010101u;
+    uint32_t wd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = sx * 4 + j - pad;
+      uint32_t v = zp4;
+      if (row >= 0 && row < h && col >= 0 && col < w) {
+        const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(x + (((int64_t)img * h + row) * w + col) * cp));
+        const uint32_t keep = (c >= 4) ? 0xffffffffu : ((1u << (8 * c)) - 1u);
+        v = (raw & keep) | (zp4 & ~keep);
+      }
+      wd[j] = v;
+    }
+    *reinterpret_cast<uint4*>(xs + t * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+}
+
+// Same layout, produced straight from the fp32 NCHW image with the input quantise
+// (quantize_utils.cc:44-52) fused in.
+__global__ void stem_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs, int n, int c, int h,
+                                     int w, int pad, int hp, int wsp, float scale, float zpf, uint32_t zp) {
+  const int64_t total = (int64_t)n * hp * wsp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int sx = (int)(t % wsp);
+    const int y = (int)((t / wsp) % hp);
+    const int img = (int)(t / ((int64_t)wsp * hp));
+    const int row = y - pad;
+    uint32_t wd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = sx * 4 + j - pad;
+      uint32_t v = zp * 0x01010101u;
+      if (row >= 0 && row < h && col >= 0 && col < w) {
+        const float* src = x + ((int64_t)img * c * h + row) * w + col;
+        v = 0;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          v |= ((ch < c) ? quant_u8_wrap(__ldg(src + (int64_t)ch * h * w), scale, zpf) : zp) << (8 * ch);
+      }
+      wd[j] = v;
+    }
+    *reinterpret_cast<uint4*>(xs + t * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+}
+
+// stem weights: ws[n][r][64], lane j = 4*px + ch
+__global__ void stem_weight_kernel(const int8_t* __restrict__ wp, int8_t* __restrict__ ws, int kc_pad, int c,
+                                   int kh, int kw, int cp) {
+  const int total = kc_pad * kh * 64;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx % 64, r = (idx / 64) % kh, n = idx / (64 * kh);
+  const int px = j >> 2, ch = j & 3;
+  ws[idx] = (px < kw && ch < c) ? wp[(((size_t)n * kh + r) * kw + px) * cp + ch] : (int8_t)0;
 }
 
 // ---- host side: tensor maps -------------------------------------------------------------
@@ -308,6 +385,7 @@ int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
   switch (bn) {
     case 32:  return launch_cfg<32, BK, (BK == 128 ? 4 : 6), IM2COL>(tmA, tmB, p, stream);
     case 64:  return launch_cfg<64, BK, (BK == 128 ? 4 : 6), IM2COL>(tmA, tmB, p, stream);
+    case 96:  return launch_cfg<96, BK, (BK == 128 ? 3 : BK == 64 ? 6 : 8), IM2COL>(tmA, tmB, p, stream);
     case 128: return launch_cfg<128, BK, (BK == 128 ? 3 : BK == 64 ? 6 : 8), IM2COL>(tmA, tmB, p, stream);
     case 192: return launch_cfg<192, BK, (BK == 128 ? 2 : BK == 64 ? 5 : 8), IM2COL>(tmA, tmB, p, stream);
     case 256: return launch_cfg<256, BK, (BK == 128 ? 2 : BK == 64 ? 4 : 8), IM2COL>(tmA, tmB, p, stream);
@@ -330,10 +408,11 @@ int launch_bk(int bk, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, co
 int pick_bn(int n) {
   if (const char* e = std::getenv("I8IE_TC_BN")) {
     const int v = std::atoi(e);
-    if (v == 32 || v == 64 || v == 128 || v == 192 || v == 256) return v;
+    if (v == 32 || v == 64 || v == 96 || v == 128 || v == 192 || v == 256) return v;
   }
   if (n <= 32) return 32;
   if (n <= 64) return 64;
+  if (n <= 96) return 96;
   if (n <= 128) return 128;
   if (n <= 192) return 192;
   if (n <= 256) return 256;
@@ -390,7 +469,7 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.cblocks = g.cp / bk;
   p.num_kb = g.kh * g.kw * p.cblocks;
-  p.kh = g.kh; p.kw = g.kw; p.stride = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
+  p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
   return launch_bk<true>(bk, bn, tmA, tmB, p, stream);
 }
@@ -400,9 +479,78 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   TcParams p;
   p.M = m; p.N = n; p.out_cp = ldy;
   p.cblocks = 1; p.num_kb = (k + 127) / 128;
-  p.kh = p.kw = 1; p.stride = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
+  p.kh = p.kw = 1; p.stride_h = p.stride_w = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   return launch_bk<false>(128, bn, tmA, tmB, p, stream);
+}
+
+
+// ---- stem path host side ---------------------------------------------------------------------
+bool tc_stem_eligible(const GemmGeom& g, int c) {
+  return c <= 4 && (g.stride == 4 || g.stride == 8) && g.kw <= 16 && g.kh <= 128 && g.pad <= g.kw &&
+         g.out_cp % 16 == 0;
+}
+
+StemGeom tc_stem_geom(const GemmGeom& g, int c) {
+  StemGeom s;
+  s.c = c;
+  s.hp = (g.oh - 1) * g.stride + g.kh;
+  s.wsp = (g.ow - 1) * (g.stride / 4) + 4;
+  s.bytes = (int64_t)g.n * s.hp * s.wsp * 16;
+  return s;
+}
+
+int tc_stem_pack_weights(const GemmGeom& g, int c, const int8_t* w_packed, int8_t* ws, cudaStream_t stream) {
+  const int total = g.n_pad * g.kh * 64;
+  stem_weight_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_packed, ws, g.n_pad, c, g.kh, g.kw, g.cp);
+  return check_launch("stem_weight_kernel");
+}
+
+int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, uint8_t* xs, int zp,
+                       cudaStream_t stream) {
+  const int64_t total = (int64_t)g.n * s.hp * s.wsp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  stem_pack_kernel<<<blocks, 256, 0, stream>>>(x, xs, g.n, s.c, g.h, g.w, g.cp, g.pad, s.hp, s.wsp, (uint32_t)zp);
+  return check_launch("stem_pack_kernel");
+}
+
+int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, uint8_t* xs, float scale, int zp,
+                           cudaStream_t stream) {
+  const int64_t total = (int64_t)g.n * s.hp * s.wsp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  stem_quantize_kernel<<<blocks, 256, 0, stream>>>(x, xs, g.n, s.c, g.h, g.w, g.pad, s.hp, s.wsp, scale, (float)zp,
+                                                 (uint32_t)zp);
+  return check_launch("stem_quantize_kernel");
+}
+
+int tc_encode_stem_act_map(CUtensorMap* tm, const uint8_t* xs, const GemmGeom& g, const StemGeom& s) {
+  static EncodeIm2colFn fn = driver_fn<EncodeIm2colFn>("cuTensorMapEncodeIm2col");
+  I8IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col entry point not available");
+  const int sw = g.stride / 4;
+  // overlapping view: "pixel" = 64-byte run starting at superpixel w; consecutive pixels are 16 bytes apart
+  cuuint64_t dims[4] = {64, (cuuint64_t)((g.ow - 1) * sw + 1), (cuuint64_t)s.hp, (cuuint64_t)g.n};
+  cuuint64_t strides[3] = {16, (cuuint64_t)s.wsp * 16, (cuuint64_t)s.hp * s.wsp * 16};
+  int lower[2] = {0, 0};
+  int upper[2] = {0, -(g.kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)g.stride, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(xs), dims, strides, lower, upper, 64,
+                  (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  I8IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col (stem view) failed (%d)", (int)r);
+  return I8IE_OK;
+}
+
+int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
+                   const EpiParams& ep, cudaStream_t stream) {
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
+  p.cblocks = 1; p.num_kb = g.kh;
+  p.kh = g.kh; p.kw = 1; p.stride_h = g.stride; p.stride_w = g.stride / 4; p.pad = 0;
+  p.H = (g.oh - 1) * g.stride + g.kh; p.W = (g.ow - 1) * (g.stride / 4) + 1; p.oh = g.oh; p.ow = g.ow;
+  p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
+  return launch_bk<true>(64, bn, tmA, tmB, p, stream);
 }
 
 int tc_read_error(int* out, bool reset) {

@@ -86,3 +86,47 @@ def test_tc_ineligible_shapes_are_refused_when_forced():
         L._forward_u8(u8_tensor_from_nchw(q, 0.03, 77), impl=2)
     # ... and taken by the SIMT kernel under auto dispatch
     L._forward_u8(u8_tensor_from_nchw(q, 0.03, 77), impl=0)
+
+
+STEM = [  # n, c, h, w, kc, k, stride, pad  (c <= 4, stride 4 or 8)
+    (2, 3, 67, 67, 32, 11, 4, 2), (2, 3, 224, 224, 96, 11, 4, 2), (2, 1, 40, 36, 16, 7, 4, 3),
+    (1, 4, 50, 50, 24, 8, 8, 0), (3, 2, 33, 31, 10, 5, 4, 1), (130, 3, 19, 19, 8, 11, 4, 2),
+]
+
+
+@pytest.mark.parametrize("geom", STEM)
+def test_tc_stem_conv(geom):
+    """Small-C strided first-layer conv (AlexNet conv1) on the tcgen05 stem path, plus the
+    fused input-quantise entry point (i8ie_conv2d_f32_u8)."""
+    from int8inferenceengine_b200 import backend as B
+    n, c, h, w_, kc, k, s, p = geom
+    rng = np.random.default_rng(sum(geom))
+    a = np.sqrt(6.0 / (c * k * k))
+    w = rng.uniform(-a, a, size=(kc, c, k, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(kc,)).astype(np.float32)
+    x = rng.uniform(-3.1, 3.1, size=(n, c, h, w_)).astype(np.float32)
+    in_scale, in_zp = np.float32(0.025), 127
+    out_scale, out_zp = np.float32(0.0518), 116
+    q = port.quantize(x, in_scale, in_zp)
+    L = make_layer("conv", w, b, (out_scale, out_zp), s, p)
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.conv2d_u8(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    oh, ow = exp.shape[2], exp.shape[3]
+    acc = torch.empty(n * oh * ow * kc, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    _no_tc_error()
+    assert L._last_impl == 3
+    assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    # fused quantise + conv straight from the fp32 image
+    acc.zero_()
+    out2 = L.forward_quantize_fused(B.tensor(x), in_scale, in_zp, acc_out=acc)
+    _no_tc_error()
+    assert out2 is not None
+    assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
+    assert np.array_equal(out2.numpy(), exp)
+    # a different input zero point exercises the physical zp border
+    q3 = port.quantize(x, np.float32(0.031), 90)
+    exp3 = port.conv2d_u8(q3, qw, qb, s, p, np.float32(0.031), 90, ws, out_scale, out_zp)
+    out3 = L._forward_u8(u8_tensor_from_nchw(q3, 0.031, 90), impl=0)
+    assert np.array_equal(out3.numpy(), exp3)
