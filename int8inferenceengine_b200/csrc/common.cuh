@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "../../include/i8ie_sm100.h"
 
@@ -66,6 +67,24 @@ __device__ __forceinline__ uint32_t requant_u8(int32_t acc, float sa, float sb, 
   return (quant >= 255.f) ? 255u : (quant < 0.f) ? 0u : (uint32_t)__float2int_rz(quant);
 }
 
+// Same result as requant_u8 with the IEEE division d / sc replaced by the classic
+// FMA-corrected quotient (rcp = RN(1/sc) hoisted out of the loop):
+//   q0 = RN(d*rcp); e = RN(d - sc*q0) (exact); q = RN(q0 + e*rcp) == RN(d / sc)
+// (Markstein's theorem: correctly rounded when rcp is the correctly rounded reciprocal, q0
+// is faithful and nothing over/underflows — the host only selects this path when sc, sa*sb
+// and the reachable |d| sit well inside the normal range, see requant_fast_ok()). The clamp
+// is done in fp32 before the truncating convert: identical to the reference's
+// (q >= 255) ? 255 : (q < 0) ? 0 : (u8)q for every input incl. NaN -> 0.
+__device__ __forceinline__ uint32_t requant_u8_fast(int32_t acc, float sa, float sb, float sc, float rcp,
+                                                    float zp_c) {
+  const float d = __fmul_rn(__fmul_rn(__int2float_rn(acc), sa), sb);
+  const float q0 = __fmul_rn(d, rcp);
+  const float e = __fmaf_rn(-sc, q0, d);
+  const float q = __fmaf_rn(e, rcp, q0);
+  const float r = fminf(fmaxf(__fadd_rn(q, zp_c), 0.f), 255.f);
+  return __float2uint_rz(r);
+}
+
 // FC's `C[i*n+j] += q_bias[j] / in.scale()` (fully_connected.cc:44): int += float.
 __device__ __forceinline__ int32_t fc_bias_add(int32_t acc, float bias_f) {
   return __float2int_rz(__fadd_rn(__int2float_rn(acc), bias_f));
@@ -111,6 +130,19 @@ __device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+
+// Host-side guard for requant_u8_fast: all scales positive, finite and comfortably normal, and
+// the largest reachable |d| = 2^31*sa*sb as well as d/sc far from overflow/underflow.
+inline bool requant_fast_ok(float sa, float sb, float sc) {
+  auto mid = [](float v) { return v > 1e-18f && v < 1e18f; };
+  if (!(mid(sa) && mid(sb) && mid(sc))) return false;
+  uint32_t bits;
+  memcpy(&bits, &sc, sizeof(bits));
+  if ((bits & 0x7fffffu) == 0x7fffffu) return false;   // Markstein's excluded divisor (significand all ones)
+  const double dmax = 2147483648.0 * (double)sa * (double)sb;
+  const double dmin = (double)sa * (double)sb;
+  return dmax < 1e30 && dmin > 1e-30 && dmax / sc < 1e30 && dmin / sc > 1e-30;
 }
 
 // epilogue parameters shared by the SIMT and tcgen05 GEMM-shaped kernels

@@ -33,10 +33,14 @@ __device__ int g_tc_error = 0;  // first protocol error seen by any tensor-core 
 
 struct TcParams {
   int M, N, out_cp;
-  int num_kb;      // K blocks of BK bytes
-  int cblocks;     // K blocks per filter tap (im2col)
+  int tiles_m, tiles_n;
+  int num_kb;      // pipeline stages consumed per tile (each = ksub sub-blocks of BK bytes)
+  int ksub;        // sub-blocks (TMA boxes per operand) per stage
+  int stages;      // ring depth
+  int cblocks;     // BK-byte channel blocks per filter tap (im2col)
   int kh, kw, stride_h, stride_w, pad, H, W, oh, ow;
   int zp_in;
+  int fast_requant;           // requant_fast_ok(sa, sb, sc)
   const int32_t* border_tab;  // [(pad+1)^4][N] or nullptr
   uint8_t* y;
   EpiParams ep;
@@ -45,165 +49,230 @@ struct TcParams {
 namespace {
 
 constexpr int BM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, 4 epilogue warps
+constexpr int kMaxStages = 16;
 
 template <int BN>
+constexpr uint32_t acc_stride() { return (BN + 31) / 32 * 32; }   // TMEM columns per accumulator buffer
+template <int BN>
 constexpr uint32_t tmem_cols() {
-  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+  return 2 * acc_stride<BN>() <= 32 ? 32 : 2 * acc_stride<BN>() <= 64 ? 64 : 2 * acc_stride<BN>() <= 128 ? 128
+         : 2 * acc_stride<BN>() <= 256 ? 256 : 512;
 }
 
-template <int BN, int BK, int STAGES>
-struct SmemLayout {
-  static constexpr int kABytes = BM * BK;
-  static constexpr int kBBytes = BN * BK;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTileBytes = STAGES * kStageBytes;
-  // after the tiles: full[STAGES], empty[STAGES], tmem_full, tmem slot, oc[BN], bias[BN]
-  static constexpr int kBarOff = kTileBytes;
-  static constexpr int kOcOff = kBarOff + (2 * STAGES + 1) * 8 + 8;
-  static constexpr int kBiasOff = kOcOff + BN * 4;
-  static constexpr int kTotal = kBiasOff + BN * 4;
-  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-byte alignment
+// control block placed after the operand ring
+template <int BN>
+struct alignas(16) TcControl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_slot;
+  uint32_t pad_[3];
+  int32_t oc[2][BN];
+  float bias[2][BN];
 };
 
-template <int BN, int BK, int STAGES, bool IM2COL>
-__global__ void __launch_bounds__(kThreads) tc_igemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB,
-                                                           const TcParams p) {
-  using L = SmemLayout<BN, BK, STAGES>;
+template <int BN, int BK>
+__host__ __device__ constexpr int stage_bytes(int ksub) { return ksub * (BM * BK + BN * BK); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
+// Persistent, warp-specialised implicit GEMM. MODE 0: A rows via a 2-D tiled map (fc);
+// MODE 1: A gathered by the TMA im2col engine (conv, incl. the stem view).
+template <int BN, int BK, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  int32_t* s_oc = reinterpret_cast<int32_t*>(smem + L::kOcOff);
-  float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
+  constexpr int kSubA = BM * BK, kSubB = BN * BK;
+  const int kStage = p.ksub * (kSubA + kSubB);
+  TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int num_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&ctl->tmem_full[b], 1);
+      ptx::mbar_init(&ctl->tmem_empty[b], kEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, tmem_cols<BN>());
-  if (warp >= 2) {
-    for (int j = threadIdx.x - 64; j < BN; j += kThreads - 64) {
-      const int n = n0 + j;
-      s_oc[j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
-      s_bias[j] = (n < p.N && p.ep.bias_f) ? __ldg(p.ep.bias_f + n) : 0.f;
-    }
-  }
+  if (warp == 1) ptx::tmem_alloc(&ctl->tmem_slot, tmem_cols<BN>());
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = ctl->tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: runs ahead across tile boundaries, the ring never drains =====
     if (lane == 0) {
-      int bw = 0, bh = 0, bn = 0;
-      if (IM2COL) {
-        const int q = m0 % p.ow, t = m0 / p.ow;
-        bw = q * p.stride_w - p.pad;
-        bh = (t % p.oh) * p.stride_h - p.pad;
-        bn = t / p.oh;
-      }
-      int cb = 0, kx = 0, ky = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (!ptx::mbar_wait(&empty_bar[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); break; }
-        ptx::mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        if (IM2COL) {
-          ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[s], cb * BK, bw, bh, bn, (uint16_t)kx, (uint16_t)ky);
-          if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
-        } else {
-          ptx::tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+      uint32_t it = 0;
+      bool alive = true;
+      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+        int bw = 0, bh = 0, bn = 0;
+        if (MODE == 1) {
+          const int q = m0 % p.ow, t = m0 / p.ow;
+          bw = q * p.stride_w - p.pad;
+          bh = (t % p.oh) * p.stride_h - p.pad;
+          bn = t / p.oh;
         }
-        ptx::tma_load_2d(sa + L::kABytes, &tmB, &full_bar[s], kb * BK, n0);
+        int cb = 0, kx = 0, ky = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+          ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)kStage);
+          uint8_t* sa = smem + (size_t)s * kStage;
+          uint8_t* sb = sa + p.ksub * kSubA;
+          for (int j = 0; j < p.ksub; ++j) {
+            const int kidx = kb * p.ksub + j;   // BK-byte sub-block index along K
+            if (MODE == 1) {
+              ptx::tma_load_im2col_4d(sa + j * kSubA, &tmA, &ctl->full[s], cb * BK, bw, bh, bn, (uint16_t)kx, (uint16_t)ky);
+              if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
+            } else {
+              ptx::tma_load_2d(sa + j * kSubA, &tmA, &ctl->full[s], kidx * BK, m0);
+            }
+            ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: one thread, accumulators ping-pong between two TMEM buffers =====
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
-      bool ok = true;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        if (!ptx::mbar_wait(&full_bar[s], ph)) { atomicCAS(&g_tc_error, 0, 2); ok = false; break; }
+      uint32_t it = 0, tcount = 0;
+      bool alive = true;
+      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1, bph = (tcount >> 1) & 1;
+        if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * L::kStageBytes);
-        const uint32_t sb = sa + L::kABytes;
+        const uint32_t d_tmem = tmem_base + buf * acc_stride<BN>();
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
+          const uint32_t sb = sa + p.ksub * kSubA;
+          for (int j = 0; j < p.ksub; ++j) {
 #pragma unroll
-        for (int k = 0; k < BK / 32; ++k) {
-          ptx::mma_i8_ss(tmem_base, ptx::make_smem_desc<BK>(sa + k * 32), ptx::make_smem_desc<BK>(sb + k * 32),
-                         idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 32; ++k) {
+              ptx::mma_i8_ss(d_tmem, ptx::make_smem_desc<BK>(sa + j * kSubA + k * 32),
+                             ptx::make_smem_desc<BK>(sb + j * kSubB + k * 32), idesc, (kb | j | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::tc_commit(&ctl->empty[s]);   // slot reusable once these MMAs have read it
         }
-        ptx::tc_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        if (alive) ptx::tc_commit(&ctl->tmem_full[buf]);
       }
-      if (ok) ptx::tc_commit(tmem_full_bar);
-      else ptx::mbar_arrive(tmem_full_bar);
+      if (!alive) {   // unblock the epilogue so that the CTA can exit
+        ptx::mbar_arrive(&ctl->tmem_full[0]);
+        ptx::mbar_arrive(&ctl->tmem_full[1]);
+      }
     }
   } else {
-    // ===== epilogue (4 warps; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)) =====
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    const bool ok = ptx::mbar_wait(tmem_full_bar, 0);
-    if (!ok) atomicCAS(&g_tc_error, 0, 3);
-    ptx::tc_fence_after();
-    // spatial border class of this output pixel -> row of the zero-point correction table
-    const int32_t* corr = nullptr;
-    if (IM2COL && p.border_tab && m < p.M) {
-      const int q = m % p.ow, pr = (m / p.ow) % p.oh;
-      const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
-      const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
-      const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
-      const int d = p.pad + 1;
-      const int cls = ((th * d + bh) * d + tw) * d + bw;
-      if (cls != 0) corr = p.border_tab + (size_t)cls * p.N;
-    }
+    const int et = threadIdx.x - 64;   // 0..127
     const float zpf = (float)p.ep.zp_out;
     const uint32_t zpo = (uint32_t)p.ep.zp_out;
-    uint8_t* yrow = p.y + (size_t)m * p.out_cp;
+    const float sa = p.ep.sa, sb = p.ep.sb, sc = p.ep.sc;
+    const float rcp = __frcp_rn(sc);
+    const bool has_bias = p.ep.bias_f != nullptr;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1, bph = (tcount >> 1) & 1;
+      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+      // stage this tile's per-channel offsets (double-buffered: one barrier per tile)
+      for (int j = et; j < BN; j += 32 * kEpiWarps) {
+        const int n = n0 + j;
+        ctl->oc[buf][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
+        ctl->bias[buf][j] = (n < p.N && has_bias) ? __ldg(p.ep.bias_f + n) : 0.f;
+      }
+      epi_bar_sync();
+      const int m = m0 + quad * 32 + lane;
+      // spatial border class of this output pixel -> row of the zero-point correction table
+      const int32_t* corr = nullptr;
+      if (MODE == 1 && p.border_tab && m < p.M) {
+        const int q = m % p.ow, pr = (m / p.ow) % p.oh;
+        const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
+        const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
+        const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
+        const int d = p.pad + 1;
+        const int cls = ((th * d + bh) * d + tw) * d + bw;
+        if (cls != 0) corr = p.border_tab + (size_t)cls * p.N;
+      }
+      const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
+      if (!ok) atomicCAS(&g_tc_error, 0, 3);
+      ptx::tc_fence_after();
+      uint8_t* yrow = p.y + (size_t)m * p.out_cp;
+      const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.out_cp) break;  // warp-uniform
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      ptx::tmem_ld_wait();
-      uint32_t packed[8];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.out_cp) break;   // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        const int32_t* soc = ctl->oc[buf] + c0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        uint32_t qv = zpo;  // pad lanes carry the zero point
-        if (n < p.N) {
-          int32_t a = (int32_t)v[j] + s_oc[c0 + j];
-          if (corr) a += p.zp_in * __ldg(corr + n);
-          if (p.ep.bias_f) a = fc_bias_add(a, s_bias[c0 + j]);
-          if (p.ep.acc_out && m < p.M) p.ep.acc_out[(size_t)m * p.N + n] = a;
-          qv = requant_u8(a, p.ep.sa, p.ep.sb, p.ep.sc, zpf);
-          if (p.ep.relu) qv = max(qv, zpo);
+        for (int j = 0; j < 32; ++j) v[j] = (uint32_t)((int32_t)v[j] + soc[j]);
+        if (corr) {   // border pixels only: zero-fill -> zero-point padding correction
+          const int nmax = p.N - (n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nmax) v[j] = (uint32_t)((int32_t)v[j] + p.zp_in * __ldg(corr + n0 + c0 + j));
         }
-        if ((j & 3) == 0) packed[j >> 2] = qv;
-        else packed[j >> 2] |= qv << (8 * (j & 3));
+        if (has_bias) {   // fully_connected.cc:44
+          const float* sbias = ctl->bias[buf] + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (uint32_t)fc_bias_add((int32_t)v[j], sbias[j]);
+        }
+        if (p.ep.acc_out && m < p.M) {   // parity-test dump
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) p.ep.acc_out[(size_t)m * p.N + n0 + c0 + j] = (int32_t)v[j];
+        }
+        if (p.fast_requant) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = requant_u8_fast((int32_t)v[j], sa, sb, sc, rcp, zpf);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = requant_u8((int32_t)v[j], sa, sb, sc, zpf);
+        }
+        if (p.ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = max(v[j], zpo);
+        }
+        if (n0 + c0 + 32 > p.N) {   // pad lanes carry the zero point (warp-uniform branch)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j >= p.N) v[j] = zpo;
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          pk[g] = v[4 * g] | (v[4 * g + 1] << 8) | (v[4 * g + 2] << 16) | (v[4 * g + 3] << 24);
+        if (m < p.M && ok) {
+          *reinterpret_cast<uint4*>(yrow + n0 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (n0 + c0 + 16 < p.out_cp)
+            *reinterpret_cast<uint4*>(yrow + n0 + c0 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
       }
-      if (m < p.M && ok) {
-        if (n0 + c0 < p.out_cp)
-          *reinterpret_cast<uint4*>(yrow + n0 + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        if (n0 + c0 + 16 < p.out_cp)
-          *reinterpret_cast<uint4*>(yrow + n0 + c0 + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-      }
+      // hand the accumulator buffer back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
     }
   }
   ptx::tc_fence_before();
@@ -365,44 +434,67 @@ int encode_im2col_4d(CUtensorMap* tm, const void* base, const GemmGeom& g, int b
   return I8IE_OK;
 }
 
-template <int BN, int BK, int STAGES, bool IM2COL>
-int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BN, BK, STAGES>;
-  static bool attr_set = false;
-  auto kern = tc_igemm_kernel<BN, BK, STAGES, IM2COL>;
-  if (!attr_set) {
-    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
-    attr_set = true;
+template <int BN, int BK, int MODE>
+int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
+  constexpr int kMaxSmem = 227 * 1024;
+  const int ctl_bytes = (int)sizeof(TcControl<BN>);
+  const int kStage = stage_bytes<BN, BK>(p.ksub);
+  int stages = (kMaxSmem - 1024 - ctl_bytes) / kStage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* e = std::getenv("I8IE_TC_STAGES")) {
+    const int v = std::atoi(e);
+    if (v >= 1 && v < stages) stages = v;
   }
-  dim3 grid((p.M + BM - 1) / BM, (p.out_cp + BN - 1) / BN);
-  kern<<<grid, kThreads, L::kDynamic, stream>>>(tmA, tmB, p);
+  I8IE_REQUIRE(stages >= 2, "tcgen05: stage of %d bytes leaves no room for a pipeline", kStage);
+  p.stages = stages;
+  const int smem = stages * kStage + ctl_bytes + 1024;
+  static int attr_smem = 0;
+  auto kern = tc_igemm_kernel<BN, BK, MODE>;
+  if (attr_smem < smem) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.out_cp + BN - 1) / BN;
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
 
-// stage counts: keep >= 2 CTAs per SM resident (epilogue/main-loop overlap) where smem allows
-template <int BK, bool IM2COL>
+template <int BK, int MODE>
 int launch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 32:  return launch_cfg<32, BK, (BK == 128 ? 4 : 6), IM2COL>(tmA, tmB, p, stream);
-    case 64:  return launch_cfg<64, BK, (BK == 128 ? 4 : 6), IM2COL>(tmA, tmB, p, stream);
-    case 96:  return launch_cfg<96, BK, (BK == 128 ? 3 : BK == 64 ? 6 : 8), IM2COL>(tmA, tmB, p, stream);
-    case 128: return launch_cfg<128, BK, (BK == 128 ? 3 : BK == 64 ? 6 : 8), IM2COL>(tmA, tmB, p, stream);
-    case 192: return launch_cfg<192, BK, (BK == 128 ? 2 : BK == 64 ? 5 : 8), IM2COL>(tmA, tmB, p, stream);
-    case 256: return launch_cfg<256, BK, (BK == 128 ? 2 : BK == 64 ? 4 : 8), IM2COL>(tmA, tmB, p, stream);
+    case 32:  return launch_cfg<32, BK, MODE>(tmA, tmB, p, stream);
+    case 64:  return launch_cfg<64, BK, MODE>(tmA, tmB, p, stream);
+    case 96:  return launch_cfg<96, BK, MODE>(tmA, tmB, p, stream);
+    case 128: return launch_cfg<128, BK, MODE>(tmA, tmB, p, stream);
+    case 192: return launch_cfg<192, BK, MODE>(tmA, tmB, p, stream);
+    case 256: return launch_cfg<256, BK, MODE>(tmA, tmB, p, stream);
   }
   set_error("tcgen05: unsupported BN %d", bn);
   return I8IE_EINVAL;
 }
 
-template <bool IM2COL>
+template <int MODE>
 int launch_bk(int bk, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
-  if (bk == 128) return launch_bn<128, IM2COL>(bn, tmA, tmB, p, stream);
-  if constexpr (IM2COL) {  // the row-tiled (fc) operand always uses 128-byte K blocks
-    if (bk == 64) return launch_bn<64, IM2COL>(bn, tmA, tmB, p, stream);
-    if (bk == 32) return launch_bn<32, IM2COL>(bn, tmA, tmB, p, stream);
+  if (bk == 128) return launch_bn<128, MODE>(bn, tmA, tmB, p, stream);
+  if constexpr (MODE == 1) {  // the row-tiled (fc) operand always uses 128-byte K blocks
+    if (bk == 64) return launch_bn<64, MODE>(bn, tmA, tmB, p, stream);
+    if (bk == 32) return launch_bn<32, MODE>(bn, tmA, tmB, p, stream);
   }
   set_error("tcgen05: unsupported BK %d", bk);
   return I8IE_EINVAL;
+}
+
+// sub-blocks per pipeline stage: short K blocks are batched so that one mbarrier round trip
+// covers >= 96..128 bytes of K (must divide the per-tap block count)
+int pick_ksub(int bk, int cblocks) {
+  if (bk == 128) return 1;
+  const int want = bk == 64 ? 2 : 4;
+  for (int k = want; k > 1; --k)
+    if (cblocks % k == 0) return k;
+  return 1;
 }
 
 int pick_bn(int n) {
@@ -468,20 +560,23 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   TcParams p;
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.cblocks = g.cp / bk;
-  p.num_kb = g.kh * g.kw * p.cblocks;
+  p.ksub = pick_ksub(bk, p.cblocks);
+  p.num_kb = g.kh * g.kw * p.cblocks / p.ksub;
   p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
-  return launch_bk<true>(bk, bn, tmA, tmB, p, stream);
+  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  return launch_bk<1>(bk, bn, tmA, tmB, p, stream);
 }
 
 int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
                  const EpiParams& ep, cudaStream_t stream) {
   TcParams p;
   p.M = m; p.N = n; p.out_cp = ldy;
-  p.cblocks = 1; p.num_kb = (k + 127) / 128;
+  p.cblocks = 1; p.ksub = 1; p.num_kb = (k + 127) / 128;
   p.kh = p.kw = 1; p.stride_h = p.stride_w = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
-  return launch_bk<false>(128, bn, tmA, tmB, p, stream);
+  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  return launch_bk<0>(128, bn, tmA, tmB, p, stream);
 }
 
 
@@ -546,11 +641,12 @@ int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
                    const EpiParams& ep, cudaStream_t stream) {
   TcParams p;
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
-  p.cblocks = 1; p.num_kb = g.kh;
+  p.cblocks = 1; p.ksub = 1; p.num_kb = g.kh;
   p.kh = g.kh; p.kw = 1; p.stride_h = g.stride; p.stride_w = g.stride / 4; p.pad = 0;
   p.H = (g.oh - 1) * g.stride + g.kh; p.W = (g.ow - 1) * (g.stride / 4) + 1; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
-  return launch_bk<true>(64, bn, tmA, tmB, p, stream);
+  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  return launch_bk<1>(64, bn, tmA, tmB, p, stream);
 }
 
 int tc_read_error(int* out, bool reset) {
