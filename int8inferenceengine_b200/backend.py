@@ -36,6 +36,23 @@ def _r16(v):
     return (int(v) + 15) // 16 * 16
 
 
+def _act_pitch(c):
+    """Channel pitch (bytes) of a u8 NHWC activation with c channels. The tcgen05 conv kernel
+    consumes one tap's channel run in K blocks of 128/64/32 bytes; wider blocks mean 4x/2x
+    fewer TMA requests per byte, so channels are padded up to the widest block that costs at
+    most ~1/3 extra K (pad lanes hold the zero point, the matching weight lanes are zero)."""
+    c = int(c)
+    if c <= 16:
+        return 16
+    if c <= 32:
+        return 32
+    for blk in (128, 64):
+        p = (c + blk - 1) // blk * blk
+        if p * 3 <= c * 4 + 2:
+            return p
+    return (c + 31) // 32 * 32
+
+
 def _need_cuda():
     if not torch.cuda.is_available():
         raise I8ieError("no CUDA device visible: the i8ie B200 backend has no CPU fallback")
@@ -65,8 +82,9 @@ class _TensorBase:
     np_dtype = None
 
     def __init__(self, storage, shape, layout="dense", geom=None, scale=1.0, zp=0):
-        self._st = storage
-        storage.views += 1
+        self._storage = storage
+        if storage is not None:
+            storage.views += 1
         self._shape = [int(s) for s in shape]
         self._layout = layout          # 'dense' | 'nhwc'
         self._geom = geom              # (n, c, h, w, cp) when layout == 'nhwc'
@@ -75,9 +93,14 @@ class _TensorBase:
 
     def __del__(self):
         try:
-            self._st.views -= 1
+            if self._storage is not None:
+                self._storage.views -= 1
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
+
+    @property
+    def _st(self):
+        return self._storage
 
     # -- the methods src/pybind11.cc:12-30 binds --------------------------------------
     def zero_point(self):
@@ -155,7 +178,28 @@ class TensorU8(_TensorBase):
     torch_dtype = torch.uint8
     np_dtype = np.uint8
 
+    def __init__(self, storage, shape, layout="dense", geom=None, scale=1.0, zp=0, deferred=None):
+        super().__init__(storage, shape, layout, geom, scale, zp)
+        self._deferred = deferred      # a _Deferred* op that has not been launched yet
+
+    @property
+    def _st(self):
+        # Deferred tensors launch their kernel the first time the bytes are needed. Until then a
+        # following relu / flatten / first-layer conv can still fold itself into that launch.
+        if self._storage is None:
+            st, layout, geom = self._deferred.launch()
+            self._storage = st
+            st.views += 1
+            self._layout, self._geom = layout, geom
+            self._deferred = None
+        return self._storage
+
+    def _pending(self, kind=None):
+        d = self._deferred if self._storage is None else None
+        return d if (d is not None and (kind is None or d.kind == kind)) else None
+
     def _dense_buf(self):
+        self._st  # noqa: B018 - materialise
         if self._layout == "dense":
             return self._st.t
         n, c, h, w, cp = self._geom
@@ -168,6 +212,12 @@ class TensorU8(_TensorBase):
         return out
 
     def _view(self, shape):
+        pool = self._pending("pool")
+        if pool is not None and not pool.out_nchw:
+            # flatten of a not-yet-launched pool: let the pool kernel write the logical (NCHW)
+            # order directly instead of NHWC + a re-layout pass (tensor.h:106-133 semantics)
+            return TensorU8(None, shape, "dense", None, self._scale, self._zp, deferred=pool.as_nchw())
+        self._st  # noqa: B018 - materialise
         if self._layout == "dense":
             return TensorU8(self._st, shape, "dense", None, self._scale, self._zp)
         n, c, h, w, cp = self._geom
@@ -176,11 +226,13 @@ class TensorU8(_TensorBase):
         # physical NHWC differs from the logical order: materialise the logical order once
         return TensorU8(_Storage(self._dense_buf()), shape, "dense", None, self._scale, self._zp)
 
-    def _as_nhwc(self, n, c, h, w):
-        """(buffer, cp) of this tensor as NHWC with pitch round_up(c,16); converts if needed."""
-        cp = _r16(c)
-        if self._layout == "nhwc" and self._geom == (n, c, h, w, cp):
-            return self._st.t, cp
+    def _as_nhwc(self, n, c, h, w, want_cp=None):
+        """(buffer, cp) of this tensor as NHWC. An NHWC tensor of the right shape is used as it
+        is, whatever its pitch (unless want_cp insists); anything else is converted once."""
+        self._st  # noqa: B018 - materialise
+        if self._layout == "nhwc" and self._geom[:4] == (n, c, h, w) and (want_cp is None or self._geom[4] == want_cp):
+            return self._st.t, self._geom[4]
+        cp = want_cp or _act_pitch(c)
         if self._layout == "dense" and h * w == 1 and cp == c:
             return self._st.t, cp
         L = _need_cuda()
@@ -189,6 +241,61 @@ class TensorU8(_TensorBase):
         check(L.i8ie_u8_nchw_to_nhwc(src.data_ptr(), out.data_ptr(), n, c, h, w, cp, self._zp, _stream()),
               "u8_nchw_to_nhwc")
         return out, cp
+
+
+class _DeferredLayer:
+    """conv / fc launch that can still absorb a following relu<u8> (functional.cc:15-26 is
+    max(y, zero_point): identical whether applied by a second kernel or in the epilogue)."""
+    kind = "layer"
+
+    def __init__(self, layer, x, relu=False):
+        self.layer, self.x, self.relu = layer, x, relu
+
+    def with_relu(self):
+        return _DeferredLayer(self.layer, self.x, True)
+
+    def launch(self):
+        y = self.layer._forward_u8(self.x, relu=self.relu or self.layer.fuse_relu)
+        return y._st, y._layout, y._geom
+
+
+class _DeferredPool:
+    kind = "pool"
+
+    def __init__(self, x, k, s, out_nchw=False):
+        self.x, self.k, self.s, self.out_nchw = x, k, s, out_nchw
+
+    def as_nchw(self):
+        return _DeferredPool(self.x, self.k, self.s, True)
+
+    def launch(self):
+        L = _need_cuda()
+        x, k, s = self.x, self.k, self.s
+        n, c, h, w = x._shape
+        oh, ow = (h - k) // s + 1, (w - k) // s + 1
+        buf, cp = x._as_nhwc(n, c, h, w)
+        out = torch.empty(n * oh * ow * (c if self.out_nchw else cp), dtype=torch.uint8, device=buf.device)
+        check(L.i8ie_maxpool_u8_nhwc(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, k, s,
+                                     1 if self.out_nchw else 0, _stream()), "maxpool_u8_nhwc")
+        if self.out_nchw:
+            return _Storage(out), "dense", None
+        return _Storage(out), "nhwc", (n, c, oh, ow, cp)
+
+
+class _DeferredQuant:
+    """Input quantise (module.py:20) that a first-layer stem convolution can fuse."""
+    kind = "quant"
+
+    def __init__(self, src, scale, zp, geom):
+        self.src, self.scale, self.zp, self.geom = src, scale, zp, geom
+
+    def launch(self):
+        L = _need_cuda()
+        n, c, h, w, cp = self.geom
+        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=self.src.buf.device)
+        check(L.i8ie_quantize_nchw_f32_nhwc_u8(self.src.buf.data_ptr(), out.data_ptr(), n, c, h, w, cp,
+                                               self.scale, self.zp, _stream()), "quantize_nchw_f32_nhwc_u8")
+        return _Storage(out), "nhwc", self.geom
 
 
 def _new_u8_nhwc(buf, n, c, h, w, cp, scale, zp, two_d=False):
@@ -232,11 +339,8 @@ def quantize(x, scale, zero_point):
     if len(shp) in (2, 4):
         n, c = shp[0], shp[1]
         h, w = (shp[2], shp[3]) if len(shp) == 4 else (1, 1)
-        cp = _r16(c)
-        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=src.device)
-        check(L.i8ie_quantize_nchw_f32_nhwc_u8(src.data_ptr(), out.data_ptr(), n, c, h, w, cp, scale, zp,
-                                               _stream()), "quantize_nchw_f32_nhwc_u8")
-        return _new_u8_nhwc(out, n, c, h, w, cp, scale, zp, two_d=(len(shp) == 2))
+        geom = (n, c, h, w, _act_pitch(c))
+        return TensorU8(None, shp, "nhwc", geom, scale, zp, deferred=_DeferredQuant(x, scale, zp, geom))
     out = torch.empty(src.numel(), dtype=torch.uint8, device=src.device)
     check(L.i8ie_quantize_f32_u8(src.data_ptr(), out.data_ptr(), src.numel(), scale, zp, _stream()),
           "quantize_f32_u8")
@@ -265,6 +369,9 @@ def relu(x):
     """relu<T> — functional.cc:5-26. u8: max(x, zero_point) on device; fp32: torch glue."""
     L = _need_cuda()
     if isinstance(x, TensorU8):
+        pend = x._pending("layer")
+        if pend is not None and not pend.relu:
+            return TensorU8(None, x._shape, x._layout, x._geom, x._scale, x._zp, deferred=pend.with_relu())
         out = torch.empty_like(x.buf)
         check(L.i8ie_relu_u8(x.buf.data_ptr(), out.data_ptr(), x.buf.numel(), x._zp, _stream()), "relu_u8")
         return TensorU8(_Storage(out), x._shape, x._layout, x._geom, x._scale, x._zp)
@@ -284,11 +391,9 @@ def max_pool2d(x, kernel_size, strides):
         raise RuntimeError("max_pool2d: window larger than input")
     oh, ow = (h - k) // s + 1, (w - k) // s + 1
     if isinstance(x, TensorU8):
-        buf, cp = x._as_nhwc(n, c, h, w)
-        out = torch.empty(n * oh * ow * cp, dtype=torch.uint8, device=buf.device)
-        check(L.i8ie_maxpool_u8_nhwc(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, k, s, 0, _stream()),
-              "maxpool_u8_nhwc")
-        return _new_u8_nhwc(out, n, c, oh, ow, cp, x._scale, x._zp)
+        cp = x._geom[4] if x._layout == "nhwc" else _act_pitch(c)
+        return TensorU8(None, [n, c, oh, ow], "nhwc", (n, c, oh, ow, cp), x._scale, x._zp,
+                        deferred=_DeferredPool(x, k, s))
     if isinstance(x, TensorF32):
         y = torch.nn.functional.max_pool2d(x.buf.view(n, c, h, w), k, s)
         return TensorF32(_Storage(y.contiguous().reshape(-1)), [n, c, oh, ow])
@@ -465,7 +570,8 @@ class _BaseLayer:
         if isinstance(x, TensorU8):
             if not self._is_quantized:
                 raise RuntimeError("layer is not converted: call prepare()/convert() before a u8 forward")
-            return self._forward_u8(x)
+            shape, geom = self._out_meta(x)     # validates the input shape now, launches later
+            return TensorU8(None, shape, "nhwc", geom, self._scale, self._zp, deferred=_DeferredLayer(self, x))
         raise TypeError("__call__(): incompatible function arguments")
 
 
@@ -506,20 +612,26 @@ class Linear(_BaseLayer):
             self._cal.sample(y)                       # fully_connected.cc:17-19
         return TensorF32(_Storage(y.reshape(-1)), [m, w.shape[0]])
 
-    def _forward_u8(self, x, acc_out=None, impl=0):
-        # Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52
-        L = _lib.load()
+    def _out_meta(self, x):
         if len(x._shape) != 2:
             raise RuntimeError("Linear expects a 2-d tensor")
         m, k = x._shape
         n, kw = self._qw_dev.shape
         if k != kw:
             raise RuntimeError(f"Linear: input has {k} features, weight expects {kw}")
-        buf, ldx = x._as_nhwc(m, k, 1, 1)
+        return [m, n], (m, n, 1, 1, _r16(n))
+
+    def _forward_u8(self, x, acc_out=None, impl=0, relu=None):
+        # Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52
+        L = _lib.load()
+        self._out_meta(x)
+        m, k = x._shape
+        n = self._qw_dev.shape[0]
+        buf, ldx = x._as_nhwc(m, k, 1, 1, want_cp=_r16(k))
         oc, bf = self._offsets(x._zp, x.scale(), False)
         ldy = _r16(n)
         out = torch.empty(m * ldy, dtype=torch.uint8, device=buf.device)
-        flags = 1 if self.fuse_relu else 0
+        flags = 1 if (self.fuse_relu if relu is None else relu) else 0
         check(L.i8ie_fc_u8(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
                            out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
                            float(self._w_scale), float(self._scale), self._zp, flags,
@@ -539,14 +651,19 @@ class Conv2d(_BaseLayer):
         self._pad = int(padding)
 
     def _pack(self):
-        L = _lib.load()
-        kc, c, kh, kw = self._qw_shape
-        self._cp = _r16(c)
-        self._kc_pad = _r16(kc)
-        wp = torch.empty(self._kc_pad * kh * kw * self._cp, dtype=torch.int8, device="cuda")
-        check(L.i8ie_pack_conv_weight(self._qw_dev.data_ptr(), wp.data_ptr(), kc, c, kh, kw, self._kc_pad,
-                                      self._cp, _stream()), "pack_conv_weight")
-        self._w_packed = wp
+        self._packed = {}       # input channel pitch -> packed [kc_pad, kh, kw, cp] s8 weights
+        self._kc_pad = _r16(self._qw_shape[0])
+
+    def _packed_for(self, cp):
+        wp = self._packed.get(cp)
+        if wp is None:
+            L = _lib.load()
+            kc, c, kh, kw = self._qw_shape
+            wp = torch.empty(self._kc_pad * kh * kw * cp, dtype=torch.int8, device="cuda")
+            check(L.i8ie_pack_conv_weight(self._qw_dev.data_ptr(), wp.data_ptr(), kc, c, kh, kw, self._kc_pad,
+                                          cp, _stream()), "pack_conv_weight")
+            self._packed[cp] = wp
+        return wp
 
     def _forward_f32(self, x):
         # Conv2d::forward_prop(Tensor<float>&&), conv2d.cc:63-98 — torch glue, TF32 off
@@ -565,8 +682,8 @@ class Conv2d(_BaseLayer):
         if p is None:
             L = _lib.load()
             kc, _, kh, kw = self._qw_shape
-            p = L.i8ie_conv2d_plan_create(n, c, h, w, cp, kc, kh, kw, self._stride, self._pad, _r16(kc),
-                                          self._w_packed.data_ptr(), self._kc_pad, impl)
+            p = L.i8ie_conv2d_plan_create(n, c, h, w, cp, kc, kh, kw, self._stride, self._pad, _act_pitch(kc),
+                                          self._packed_for(cp).data_ptr(), self._kc_pad, impl)
             if not p:
                 raise I8ieError(f"conv2d_plan_create failed: {_lib.last_error()}")
             self._plans[key] = p
@@ -580,9 +697,7 @@ class Conv2d(_BaseLayer):
         except Exception:  # noqa: BLE001
             pass
 
-    def _forward_u8(self, x, acc_out=None, impl=0):
-        # Conv2d::forward_prop(Tensor<u8>&&), conv2d.cc:100-142
-        L = _lib.load()
+    def _out_meta(self, x):
         if len(x._shape) != 4:
             raise RuntimeError("Conv2d expects a 4-d tensor")
         n, c, h, w = x._shape
@@ -591,21 +706,37 @@ class Conv2d(_BaseLayer):
             raise RuntimeError(f"Conv2d: input has {c} channels, weight expects {cw}")
         if h + 2 * self._pad < kh or w + 2 * self._pad < kw:
             raise RuntimeError("Conv2d: kernel larger than padded input")
-        buf, cp = x._as_nhwc(n, c, h, w)
         oh = (h - kh + 2 * self._pad) // self._stride + 1
         ow = (w - kw + 2 * self._pad) // self._stride + 1
+        return [n, kc, oh, ow], (n, kc, oh, ow, _act_pitch(kc))
+
+    def _forward_u8(self, x, acc_out=None, impl=0, relu=None):
+        # Conv2d::forward_prop(Tensor<u8>&&), conv2d.cc:100-142
+        L = _lib.load()
+        (n, kc, oh, ow), _ = self._out_meta(x)
+        _, c, h, w = x._shape
+        kh, kw = self._qw_shape[2], self._qw_shape[3]
+        relu = self.fuse_relu if relu is None else relu
+        quant = x._pending("quant") if (impl == 0 and acc_out is None) else None
+        if quant is not None:
+            # the input is a not-yet-launched quantise of an fp32 image: a stem-eligible first
+            # layer consumes the fp32 image directly (quantise fused into its operand staging)
+            y = self.forward_quantize_fused(quant.src, quant.scale, quant.zp, relu=relu)
+            if y is not None:
+                return y
+        buf, cp = x._as_nhwc(n, c, h, w)
         oc, _ = self._offsets(x._zp, x.scale(), True)
-        out_cp = _r16(kc)
+        out_cp = _act_pitch(kc)
         out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=buf.device)
         plan = self._plan(n, c, h, w, cp, impl)
         self._last_impl = int(L.i8ie_conv2d_plan_impl(plan))   # 1 SIMT, 2 tcgen05 im2col, 3 tcgen05 stem
-        flags = 1 if self.fuse_relu else 0
+        flags = 1 if relu else 0
         check(L.i8ie_conv2d_u8(plan, buf.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
                                float(self._w_scale), float(self._scale), x._zp, self._zp, flags,
                                acc_out.data_ptr() if acc_out is not None else None, _stream()), "conv2d_u8")
         return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
 
-    def forward_quantize_fused(self, x, in_scale, in_zp, acc_out=None):
+    def forward_quantize_fused(self, x, in_scale, in_zp, acc_out=None, relu=None):
         """Module.__call__'s input quantise (module.py:20) fused into this convolution
         (i8ie_conv2d_f32_u8). Only stem-eligible layers (C <= 4, stride 4/8) support it;
         returns None otherwise so the caller falls back to quantize() + __call__()."""
@@ -623,12 +754,45 @@ class Conv2d(_BaseLayer):
         oh = (h - kh + 2 * self._pad) // self._stride + 1
         ow = (w - kw + 2 * self._pad) // self._stride + 1
         oc, _ = self._offsets(int(in_zp), in_scale, True)
-        out_cp = _r16(kc)
+        out_cp = _act_pitch(kc)
         out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=x.buf.device)
-        flags = 1 if self.fuse_relu else 0
+        flags = 1 if (self.fuse_relu if relu is None else relu) else 0
         check(L.i8ie_conv2d_f32_u8(plan, x.buf.data_ptr(), in_scale, int(in_zp), out.data_ptr(), oc.data_ptr(),
                                    float(self._w_scale), float(self._scale), self._zp, flags,
                                    acc_out.data_ptr() if acc_out is not None else None, _stream()),
               "conv2d_f32_u8")
         self._last_impl = 3
         return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
+
+
+# ---- CUDA-graph replay of a whole quantised forward (used by api.Module.__call__) ------------
+
+def graphable(x):
+    return isinstance(x, TensorF32) and torch.cuda.is_available()
+
+
+def capture_forward(fn, x):
+    """Captures fn(Tensor(static copy of x)) into a CUDA graph. The warm-up calls before this
+    have already created every plan / offset table / packed weight, so nothing allocates
+    through the C ABI or synchronises while the stream is capturing."""
+    from .api import Tensor
+    static_in = torch.empty_like(x.buf)
+    static_in.copy_(x.buf)
+    torch.cuda.synchronize()
+    before = _lib.launch_count()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fn(Tensor(TensorF32(_Storage(static_in), x._shape)))
+        out_buf = out.data.buf
+    kernels = _lib.launch_count() - before
+    if not isinstance(out.data, TensorF32):
+        raise RuntimeError("forward() did not return a dequantised tensor")
+    return {"graph": g, "static_in": static_in, "out_buf": out_buf, "out_shape": list(out.data._shape),
+            "kernels": int(kernels), "replays": 0}
+
+
+def replay_forward(st, x):
+    st["static_in"].copy_(x.buf, non_blocking=True)
+    st["graph"].replay()
+    st["replays"] += 1
+    return TensorF32(_Storage(st["out_buf"].clone()), st["out_shape"])
