@@ -65,6 +65,7 @@ struct i8ie_conv_plan {
   uint8_t* stem_x;      // bordered superpixel image, rewritten by every call
   int8_t* stem_w;       // [kc_pad][kh][64]
   CUtensorMap tmA_stem;
+  bool stem2;           // smem-resident-row kernel (stride 4, narrow rows)
 };
 
 static void plan_free(i8ie_conv_plan* p) {
@@ -116,8 +117,9 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   int rc = I8IE_OK;
   if (p->impl == 3) {
     p->stem = tc_stem_geom(g, c);
+    p->stem2 = tc_stem2_eligible(g, c) && std::getenv("I8IE_NO_STEM2") == nullptr;
     p->bk = 64;
-    p->bn = tc_pick_bn(g.N);
+    p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
     if (cudaMalloc(&p->stem_x, (size_t)p->stem.bytes) != cudaSuccess ||
         cudaMalloc(&p->stem_w, (size_t)kc_pad * kh * 64) != cudaSuccess) {
       set_error("conv2d_plan_create: cudaMalloc of the stem buffers failed");
@@ -140,7 +142,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   }
   if (rc == I8IE_OK && p->impl == 2) {
     p->bk = tc_conv_bk(g);
-    p->bn = tc_pick_bn(g.N);
+    p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
     rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->bn);
     const int tab = tc_border_table_size(g);
     if (rc == I8IE_OK && tab > 0) {
@@ -175,6 +177,8 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   if (plan->impl == 3) {
     int rc = tc_stem_pack_input(plan->g, plan->stem, x, plan->stem_x, zp_in, (cudaStream_t)stream);
     if (rc != I8IE_OK) return rc;
+    if (plan->stem2)
+      return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
     return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
   }
   if (plan->impl == 2) {
@@ -198,6 +202,8 @@ int i8ie_conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, float in_scale
   EpiParams ep{oc, nullptr, in_scale, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
   int rc = tc_stem_quantize_input(plan->g, plan->stem, x_nchw, plan->stem_x, in_scale, in_zp, (cudaStream_t)stream);
   if (rc != I8IE_OK) return rc;
+  if (plan->stem2)
+    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
   return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
 }
 

@@ -51,6 +51,9 @@ int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, u
 int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, uint8_t* xs, float scale, int zp,
                            cudaStream_t stream);
 int tc_encode_stem_act_map(CUtensorMap* tm, const uint8_t* xs, const GemmGeom& g, const StemGeom& s);
+bool tc_stem2_eligible(const GemmGeom& g, int c);
+int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const CUtensorMap& tmB, int bn,
+                    uint8_t* y, const EpiParams& ep, cudaStream_t stream);
 int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
                    const EpiParams& ep, cudaStream_t stream);
 

@@ -49,8 +49,8 @@ struct TcParams {
 namespace {
 
 constexpr int BM = 128;
-constexpr int kEpiWarps = 4;
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, 4 epilogue warps
+constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant (warp % 4), alternating 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 constexpr int kMaxStages = 16;
 
 template <int BN>
@@ -78,6 +78,87 @@ template <int BN, int BK>
 __host__ __device__ constexpr int stage_bytes(int ksub) { return ksub * (BM * BK + BN * BK); }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
+
+// One output row (= one TMEM lane) of a 128 x BN accumulator tile: + oc, [border correction],
+// [fc float bias], requantise, [relu], packed u8 store. m < 0: row is padding (nothing stored).
+// Two warps share each TMEM lane quadrant and take alternate 32-column chunks (`half`).
+// `s_oc` / `s_bias` are shared-memory addresses of this tile's staged per-channel terms.
+template <int BN>
+__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, long long m, int n0,
+                                             uint32_t s_oc, uint32_t s_bias, const int32_t* corr, float rcp,
+                                             int half) {
+  const float zpf = (float)p.ep.zp_out;
+  const float sa = p.ep.sa, sb = p.ep.sb, sc = p.ep.sc;
+  const bool has_bias = p.ep.bias_f != nullptr;
+  // relu<u8> is max(y, zero_point): folded into the lower clamp bound (functional.cc:22-23)
+  const float lo = p.ep.relu ? zpf : 0.f;
+  uint8_t* yrow = p.y + (size_t)(m < 0 ? 0 : m) * p.out_cp;
+#pragma unroll 1
+  for (int c0 = half * 32; c0 < BN; c0 += 64) {
+    if (n0 + c0 >= p.out_cp) break;   // warp-uniform
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 o = ptx::lds128(s_oc + (uint32_t)(c0 + 4 * g) * 4);
+      v[4 * g] += o.x; v[4 * g + 1] += o.y; v[4 * g + 2] += o.z; v[4 * g + 3] += o.w;
+    }
+    if (corr) {   // border pixels only: zero-fill -> zero-point padding correction
+      const int nmax = p.N - (n0 + c0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nmax) v[j] = (uint32_t)((int32_t)v[j] + p.zp_in * __ldg(corr + n0 + c0 + j));
+    }
+    if (has_bias) {   // fully_connected.cc:44
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 b = ptx::lds128(s_bias + (uint32_t)(c0 + 4 * g) * 4);
+        v[4 * g] = (uint32_t)fc_bias_add((int32_t)v[4 * g], __uint_as_float(b.x));
+        v[4 * g + 1] = (uint32_t)fc_bias_add((int32_t)v[4 * g + 1], __uint_as_float(b.y));
+        v[4 * g + 2] = (uint32_t)fc_bias_add((int32_t)v[4 * g + 2], __uint_as_float(b.z));
+        v[4 * g + 3] = (uint32_t)fc_bias_add((int32_t)v[4 * g + 3], __uint_as_float(b.w));
+      }
+    }
+    if (p.ep.acc_out && m >= 0) {   // parity-test dump
+      for (int j = 0; j < 32; ++j)
+        if (n0 + c0 + j < p.N) p.ep.acc_out[(size_t)m * p.N + n0 + c0 + j] = (int32_t)v[j];
+    }
+    if (p.fast_requant) {
+      // exact requantise (see requant_u8_fast); the truncating convert is a round-down add of
+      // 2^23, which leaves floor(r) in the low mantissa byte (r is already clamped to [0,255])
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = __fmul_rn(__fmul_rn(__int2float_rn((int32_t)v[j]), sa), sb);
+        const float q0 = __fmul_rn(d, rcp);
+        const float e = __fmaf_rn(-sc, q0, d);
+        const float q = __fmaf_rn(e, rcp, q0);
+        const float r = fminf(fmaxf(__fadd_rn(q, zpf), lo), 255.f);
+        v[j] = __float_as_uint(__fadd_rd(r, 8388608.f));
+      }
+    } else {
+      const uint32_t zlo = p.ep.relu ? (uint32_t)p.ep.zp_out : 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = max(requant_u8((int32_t)v[j], sa, sb, sc, zpf), zlo);
+    }
+    if (n0 + c0 + 32 > p.N) {   // pad lanes carry the zero point (warp-uniform branch)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + c0 + j >= p.N) v[j] = (uint32_t)p.ep.zp_out;
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)   // low bytes of four registers -> one word
+      pk[g] = __byte_perm(__byte_perm(v[4 * g], v[4 * g + 1], 0x0040), __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x0040),
+                          0x5410);
+    if (m >= 0) {
+      *reinterpret_cast<uint4*>(yrow + n0 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (n0 + c0 + 16 < p.out_cp)
+        *reinterpret_cast<uint4*>(yrow + n0 + c0 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+}
 
 // Persistent, warp-specialised implicit GEMM. MODE 0: A rows via a 2-D tiled map (fc);
 // MODE 1: A gathered by the TMA im2col engine (conv, incl. the stem view).
@@ -183,13 +264,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       }
     }
   } else {
-    // ===== epilogue: 4 warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
+    // ===== epilogue: 8 warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
     const int quad = warp & 3;
     const int et = threadIdx.x - 64;   // 0..127
-    const float zpf = (float)p.ep.zp_out;
-    const uint32_t zpo = (uint32_t)p.ep.zp_out;
-    const float sa = p.ep.sa, sb = p.ep.sb, sc = p.ep.sc;
-    const float rcp = __frcp_rn(sc);
+    const float rcp = __frcp_rn(p.ep.sc);
     const bool has_bias = p.ep.bias_f != nullptr;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -217,59 +295,152 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
       if (!ok) atomicCAS(&g_tc_error, 0, 3);
       ptx::tc_fence_after();
-      uint8_t* yrow = p.y + (size_t)m * p.out_cp;
       const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.out_cp) break;   // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
-        ptx::tmem_ld_wait();
-        const int32_t* soc = ctl->oc[buf] + c0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (uint32_t)((int32_t)v[j] + soc[j]);
-        if (corr) {   // border pixels only: zero-fill -> zero-point padding correction
-          const int nmax = p.N - (n0 + c0);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nmax) v[j] = (uint32_t)((int32_t)v[j] + p.zp_in * __ldg(corr + n0 + c0 + j));
-        }
-        if (has_bias) {   // fully_connected.cc:44
-          const float* sbias = ctl->bias[buf] + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (uint32_t)fc_bias_add((int32_t)v[j], sbias[j]);
-        }
-        if (p.ep.acc_out && m < p.M) {   // parity-test dump
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) p.ep.acc_out[(size_t)m * p.N + n0 + c0 + j] = (int32_t)v[j];
-        }
-        if (p.fast_requant) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = requant_u8_fast((int32_t)v[j], sa, sb, sc, rcp, zpf);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = requant_u8((int32_t)v[j], sa, sb, sc, zpf);
-        }
-        if (p.ep.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = max(v[j], zpo);
-        }
-        if (n0 + c0 + 32 > p.N) {   // pad lanes carry the zero point (warp-uniform branch)
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j >= p.N) v[j] = zpo;
-        }
-        uint32_t pk[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          pk[g] = v[4 * g] | (v[4 * g + 1] << 8) | (v[4 * g + 2] << 16) | (v[4 * g + 3] << 24);
-        if (m < p.M && ok) {
-          *reinterpret_cast<uint4*>(yrow + n0 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          if (n0 + c0 + 16 < p.out_cp)
-            *reinterpret_cast<uint4*>(yrow + n0 + c0 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
+      epilogue_row<BN>(p, t_row, (m < p.M && ok) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[buf]),
+                       ptx::smem_u32(ctl->bias[buf]), corr, rcp, (warp - 2) >> 2);
       // hand the accumulator buffer back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
+}
+
+
+// ---- stem2: smem-resident stem rows, sliding windows expressed by overlapping descriptors ---
+// For stride-4 stems the window of output pixel q starts at superpixel q, i.e. 16 bytes after
+// the window of q-1: exactly the fixed row pitch of a NO-SWIZZLE K-major UMMA core matrix
+// (8 rows x 16 B, rows 16 B apart). So the raw stem rows are copied to shared memory ONCE and
+// the A descriptor (LBO = 16 B between the two 16-byte K chunks, SBO = 128 B between 8-row
+// groups) walks them as 64 overlapping windows — no im2col copy, no duplicated fetch.
+// An M=128 tile is two output rows (p, p+1) x 64 columns: input rows 4 apart are stored
+// exactly 1024 B apart (region = row % 4, slot = row / 4), which keeps SBO uniform across the
+// switch from output row p to p+1. The whole packed weight [kh][BN x 64 B] stays resident.
+struct Stem2Params {
+  int n_img, oh, ow, kh, hp, wsp;
+  int pairs;        // ceil(oh / 2) output-row pairs per image
+  int nsl;          // 1 KB slots per region = ceil((kh + 4) / 4)
+  int stages;
+  const uint8_t* xs;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
+                                                               const TcParams p, const Stem2Params sp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int w_bytes = sp.kh * BN * 64;          // resident weights, one [BN x 64 B] SW64 tile per filter row
+  const int a_stage = 4 * sp.nsl * 1024;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + w_bytes;
+  TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(sA + (size_t)sp.stages * a_stage);
+  uint64_t* w_full = &ctl->full[kMaxStages - 1];   // the ring never uses more than kMaxStages-1 slots here
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = sp.n_img * sp.pairs;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < sp.stages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    ptx::mbar_init(w_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&ctl->tmem_full[b], 1);
+      ptx::mbar_init(&ctl->tmem_empty[b], kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&ctl->tmem_slot, tmem_cols<BN>());
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_slot;
+  const int rows_per_tile = sp.kh + 4;
+  const uint32_t row_bytes = (uint32_t)sp.wsp * 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights once
+      ptx::mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
+      for (int r = 0; r < sp.kh; ++r) ptx::tma_load_2d(sW + (size_t)r * BN * 64, &tmB, w_full, r * 64, 0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
+        const int s = it % sp.stages;
+        const uint32_t ph = (it / sp.stages) & 1;
+        if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); break; }
+        const int i0 = 4 * p0;
+        int nrows = sp.hp - i0;
+        if (nrows > rows_per_tile) nrows = rows_per_tile;
+        ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)nrows * row_bytes);
+        uint8_t* st = sA + (size_t)s * a_stage;
+        const uint8_t* src = sp.xs + ((size_t)img * sp.hp + i0) * row_bytes;
+        for (int i = 0; i < nrows; ++i)
+          ptx::bulk_load_1d(st + (size_t)((i & 3) * sp.nsl + (i >> 2)) * 1024, src + (size_t)i * row_bytes, row_bytes,
+                            &ctl->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
+      bool alive = ptx::mbar_wait(w_full, 0);
+      if (!alive) atomicCAS(&g_tc_error, 0, 5);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+        const int s = it % sp.stages;
+        const uint32_t ph = (it / sp.stages) & 1;
+        if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
+        if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * acc_stride<BN>();
+        const uint32_t sa0 = ptx::smem_u32(sA + (size_t)s * a_stage);
+        const uint32_t sw0 = ptx::smem_u32(sW);
+        for (int r = 0; r < sp.kh; ++r) {
+          const uint32_t a_row = sa0 + (uint32_t)((r & 3) * sp.nsl + (r >> 2)) * 1024u;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            ptx::mma_i8_ss(d_tmem, ptx::make_smem_desc_nosw(a_row + k * 32, 16, 128),
+                           ptx::make_smem_desc<64>(sw0 + (uint32_t)r * BN * 64 + k * 32), idesc, (r | k) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::tc_commit(&ctl->empty[s]);
+        ptx::tc_commit(&ctl->tmem_full[buf]);
+      }
+      if (!alive) {
+        ptx::mbar_arrive(&ctl->tmem_full[0]);
+        ptx::mbar_arrive(&ctl->tmem_full[1]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int et = threadIdx.x - 64;
+    const float rcp = __frcp_rn(p.ep.sc);
+    // per-channel offsets are the same for every tile (single N tile)
+    for (int j = et; j < BN; j += 32 * kEpiWarps) {
+      ctl->oc[0][j] = (j < p.N) ? __ldg(p.ep.oc + j) : 0;
+      ctl->bias[0][j] = 0.f;
+    }
+    epi_bar_sync();
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+      const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
+      const int l = quad * 32 + lane;            // TMEM lane = tile row
+      const int prow = p0 + (l >> 6), q = l & 63;
+      const bool valid = (prow < sp.oh) && (q < sp.ow);
+      const long long m = valid ? ((long long)img * sp.oh + prow) * sp.ow + q : -1ll;
+      const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
+      if (!ok) atomicCAS(&g_tc_error, 0, 3);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
+      epilogue_row<BN>(p, t_row, ok ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]), ptx::smem_u32(ctl->bias[0]), nullptr, rcp,
+                       (warp - 2) >> 2);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
@@ -647,6 +818,57 @@ int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
   return launch_bk<1>(64, bn, tmA, tmB, p, stream);
+}
+
+bool tc_stem2_eligible(const GemmGeom& g, int c) {
+  // stride 4 (16-byte window step), both row windows inside one 1 KB slot, resident weights fit
+  const int wsp = (g.ow - 1) + 4;
+  return tc_stem_eligible(g, c) && g.stride == 4 && wsp <= 64 && g.kh <= 12 && g.out_cp <= 128 &&
+         g.kh * tc_pick_bn(g.out_cp) * 64 <= 100 * 1024;
+}
+
+template <int BN>
+int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const CUtensorMap& tmB, TcParams p,
+                    cudaStream_t stream) {
+  Stem2Params sp;
+  sp.n_img = g.n; sp.oh = g.oh; sp.ow = g.ow; sp.kh = g.kh; sp.hp = s.hp; sp.wsp = s.wsp;
+  sp.pairs = (g.oh + 1) / 2;
+  sp.nsl = (g.kh + 4 + 3) / 4;
+  sp.xs = xs;
+  const int w_bytes = g.kh * BN * 64;
+  const int a_stage = 4 * sp.nsl * 1024;
+  const int ctl_bytes = (int)sizeof(TcControl<BN>);
+  int stages = (227 * 1024 - 1024 - ctl_bytes - w_bytes) / a_stage;
+  if (stages > 6) stages = 6;
+  I8IE_REQUIRE(stages >= 2, "stem2: not enough shared memory for the row ring");
+  sp.stages = stages;
+  const int smem = w_bytes + stages * a_stage + ctl_bytes + 1024;
+  static int attr_smem = 0;
+  auto kern = tc_stem2_kernel<BN>;
+  if (attr_smem < smem) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int tiles = sp.n_img * sp.pairs;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, smem, stream>>>(tmB, p, sp);
+  return check_launch("tc_stem2_kernel");
+}
+
+int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const CUtensorMap& tmB, int bn,
+                    uint8_t* y, const EpiParams& ep, cudaStream_t stream) {
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
+  p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
+  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  switch (bn) {
+    case 32:  return launch_stem2_bn<32>(g, s, xs, tmB, p, stream);
+    case 64:  return launch_stem2_bn<64>(g, s, xs, tmB, p, stream);
+    case 96:  return launch_stem2_bn<96>(g, s, xs, tmB, p, stream);
+    case 128: return launch_stem2_bn<128>(g, s, xs, tmB, p, stream);
+  }
+  set_error("stem2: unsupported BN %d", bn);
+  return I8IE_EINVAL;
 }
 
 int tc_read_error(int* out, bool reset) {

@@ -50,6 +50,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   return true;
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+
 // ---- TMA ---------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -69,6 +75,13 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
       "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
+}
+
+// 1-D bulk copy global -> shared (size multiple of 16 bytes), completes on the mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---- tcgen05 -------------------------------------------------------------------
@@ -132,6 +145,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)((SW * 8) >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= layout << 61;
+  return d;
+}
+
+// No-swizzle K-major operand: core matrices of 8 rows x 16 bytes with rows 16 bytes apart;
+// `lbo` = byte distance between the two 16-byte K chunks of one MMA, `sbo` = between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 
