@@ -333,7 +333,21 @@ __global__ void __launch_bounds__(kThreads) zp_offsets_kernel(const int8_t* __re
   if (row >= n) return;
   const int8_t* wr = qw + (int64_t)row * k;
   long long s = 0, sabs = 0;
-  for (int i = lane; i < k; i += 32) {
+  int i0 = 0;
+  if ((k & 15) == 0 && ((reinterpret_cast<uintptr_t>(wr) & 15) == 0)) {   // 128-bit loads, byte sums via dp4a
+    int ps = 0;
+    unsigned pa = 0;
+    for (int i = lane * 16; i < k; i += 32 * 16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(wr + i));
+      ps = __dp4a((int)v.x, 0x01010101, ps); ps = __dp4a((int)v.y, 0x01010101, ps);
+      ps = __dp4a((int)v.z, 0x01010101, ps); ps = __dp4a((int)v.w, 0x01010101, ps);
+      pa = __dp4a(__vabs4(v.x), 0x01010101u, pa); pa = __dp4a(__vabs4(v.y), 0x01010101u, pa);
+      pa = __dp4a(__vabs4(v.z), 0x01010101u, pa); pa = __dp4a(__vabs4(v.w), 0x01010101u, pa);
+    }
+    s = ps; sabs = pa;
+    i0 = k;
+  }
+  for (int i = i0 + lane; i < k; i += 32) {
     const int v = wr[i];
     s += v;
     sabs += (v < 0) ? -v : v;

@@ -220,17 +220,15 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
   const bool eligible = !tc_disabled() && k >= 32;
   I8IE_REQUIRE(!(impl == 2 && !eligible), "fc_u8: shape not eligible for the tcgen05 kernel");
   if (impl != 1 && eligible) {
-    // one M tile: favour narrow N tiles so that enough CTAs stream the weights
-    int bn = tc_pick_bn(n);
-    if (m <= 128) bn = (n >= 2048) ? 32 : (n >= 512 ? 64 : bn);
-    else if (m <= 512 && bn > 128) bn = 128;
+    int bn, splits, kb_per;
+    tc_fc_config(m, ldy, k, &bn, &splits, &kb_per);
     CUtensorMap tmA, tmB;
     int rc = g_fc_maps.get(x, m, k, ldx, 1, &tmA, [&](CUtensorMap* mp) { return tc_encode_act_map_rows(mp, x, m, k, ldx); });
     if (rc != I8IE_OK) return rc;
     rc = g_fc_maps.get(w, n_pad, ldw, bn, 2, &tmB,
                        [&](CUtensorMap* mp) { return tc_encode_weight_map(mp, w, n_pad, ldw, 128, bn); });
     if (rc != I8IE_OK) return rc;
-    return launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, y, ep, (cudaStream_t)stream);
+    return launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream);
   }
   GemmGeom g;
   g.n = m; g.h = 1; g.w = 1; g.cp = ldx;

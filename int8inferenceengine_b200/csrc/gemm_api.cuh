@@ -34,8 +34,9 @@ int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& 
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx);
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream);
-int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
-                 const EpiParams& ep, cudaStream_t stream);
+void tc_fc_config(int m, int ldy, int k, int* bn, int* splits, int* kb_per);
+int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
+                 int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream);
 int tc_read_error(int* out, bool reset);
 
 // stem path (small-C strided first-layer convs), see tc_gemm.cu

@@ -44,6 +44,10 @@ struct TcParams {
   const int32_t* border_tab;  // [(pad+1)^4][N] or nullptr
   uint8_t* y;
   EpiParams ep;
+  // split-K (small-M fc): each tile covers kb_per stages of K and dumps raw s32 partials
+  int splits, kb_per;
+  int32_t* ws;                // [splits][M][ws_ld]
+  int ws_ld;
 };
 
 namespace {
@@ -173,7 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int mn_tiles = p.tiles_m * p.tiles_n;
+  const int num_tiles = mn_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -200,7 +205,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       uint32_t it = 0;
       bool alive = true;
       for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+        const int split = tile / mn_tiles, mn = tile % mn_tiles;
+        const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+        const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
         int bw = 0, bh = 0, bn = 0;
         if (MODE == 1) {
           const int q = m0 % p.ow, t = m0 / p.ow;
@@ -208,8 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
           bh = (t % p.oh) * p.stride_h - p.pad;
           bn = t / p.oh;
         }
-        int cb = 0, kx = 0, ky = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        int cb = 0, kx = 0, ky = 0;   // (split-K is only used with MODE 0, where these stay 0)
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
@@ -240,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * acc_stride<BN>();
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int kb0 = (tile / mn_tiles) * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
 #pragma unroll
             for (int k = 0; k < BK / 32; ++k) {
               ptx::mma_i8_ss(d_tmem, ptx::make_smem_desc<BK>(sa + j * kSubA + k * 32),
-                             ptx::make_smem_desc<BK>(sb + j * kSubB + k * 32), idesc, (kb | j | k) != 0 ? 1u : 0u);
+                             ptx::make_smem_desc<BK>(sb + j * kSubB + k * 32), idesc, ((kb - kb0) | j | k) != 0 ? 1u : 0u);
             }
           }
           ptx::tc_commit(&ctl->empty[s]);   // slot reusable once these MMAs have read it
@@ -272,7 +280,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1, bph = (tcount >> 1) & 1;
-      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+      const int split = tile / mn_tiles, mn = tile % mn_tiles;
+      const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+      if (p.splits > 1) {
+        // split-K: dump the raw partial accumulators; fc_splitk_reduce_kernel finishes the job
+        const int m = m0 + quad * 32 + lane;
+        const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
+        if (!ok) atomicCAS(&g_tc_error, 0, 3);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
+        int32_t* wrow = p.ws + ((size_t)split * p.M + (m < p.M ? m : 0)) * p.ws_ld + n0;
+#pragma unroll 1
+        for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 64) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+          ptx::tmem_ld_wait();
+          if (m < p.M && ok) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+        continue;
+      }
       // stage this tile's per-channel offsets (double-buffered: one barrier per tile)
       for (int j = et; j < BN; j += 32 * kEpiWarps) {
         const int n = n0 + j;
@@ -550,6 +583,77 @@ __global__ void stem_weight_kernel(const int8_t* __restrict__ wp, int8_t* __rest
   ws[idx] = (px < kw && ch < c) ? wp[(((size_t)n * kh + r) * kw + px) * cp + ch] : (int8_t)0;
 }
 
+
+// split-K finish: y[m][n] = requant(sum_s ws[s][m][n] + oc[n] (+ float bias)).
+// One thread per (row, 4 channels): a warp reads 512 contiguous bytes of every split (fully
+// coalesced), eight independent 128-bit loads in flight per thread. Integer adds commute, so
+// the reduction order is irrelevant to the result.
+__global__ void __launch_bounds__(256) fc_splitk_reduce_kernel(const int32_t* __restrict__ ws, int splits, int M,
+                                                               int N, int ws_ld, int ldy, uint8_t* __restrict__ y,
+                                                               const EpiParams ep, int fast) {
+  const int quads = ldy >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * quads) return;
+  const int m = (int)(idx / quads), n4 = (int)(idx % quads) * 4;
+  const size_t split_stride = (size_t)M * ws_ld;
+  const int32_t* src = ws + (size_t)m * ws_ld + n4;
+  int4 a = make_int4(0, 0, 0, 0);
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    int4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const int4*>(src + (size_t)(s + j) * split_stride));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+  }
+  for (; s < splits; ++s) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(src + (size_t)s * split_stride));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const float zpf = (float)ep.zp_out;
+  const float rcp = __frcp_rn(ep.sc);
+  const uint32_t zlo = ep.relu ? (uint32_t)ep.zp_out : 0u;
+  const int32_t acc[4] = {a.x, a.y, a.z, a.w};
+  uint32_t word = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n4 + j;
+    uint32_t q = (uint32_t)ep.zp_out;   // pad lanes carry the zero point
+    if (n < N) {
+      int32_t v = acc[j] + __ldg(ep.oc + n);
+      if (ep.bias_f) v = fc_bias_add(v, __ldg(ep.bias_f + n));
+      if (ep.acc_out) ep.acc_out[(size_t)m * N + n] = v;
+      const uint32_t r = fast ? requant_u8_fast(v, ep.sa, ep.sb, ep.sc, rcp, zpf) : requant_u8(v, ep.sa, ep.sb, ep.sc, zpf);
+      q = max(r, zlo);
+    }
+    word |= q << (8 * j);
+  }
+  *reinterpret_cast<uint32_t*>(y + (size_t)m * ldy + n4) = word;
+}
+
+// process-wide split-K scratch, grown outside of stream capture (the first eager call sizes it)
+std::mutex g_ws_mu;
+int32_t* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+
+int ensure_workspace(size_t bytes, cudaStream_t stream, int32_t** out) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  if (bytes > g_ws_bytes) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &st);
+    I8IE_REQUIRE(st == cudaStreamCaptureStatusNone,
+                 "fc split-K workspace must grow (%zu bytes) while the stream is capturing: run the shape once eagerly first", bytes);
+    I8IE_CUDA_OK(cudaDeviceSynchronize());
+    if (g_ws) cudaFree(g_ws);
+    g_ws = nullptr; g_ws_bytes = 0;
+    const size_t want = bytes + (bytes >> 2);
+    I8IE_CUDA_OK(cudaMalloc(&g_ws, want));
+    g_ws_bytes = want;
+  }
+  *out = g_ws;
+  return I8IE_OK;
+}
+
 // ---- host side: tensor maps -------------------------------------------------------------
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -627,7 +731,8 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaS
   }
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.out_cp + BN - 1) / BN;
-  const int tiles = p.tiles_m * p.tiles_n;
+  if (p.splits < 1) { p.splits = 1; p.kb_per = p.num_kb; }
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
@@ -728,7 +833,7 @@ int tc_pick_bn(int n) { return pick_bn(n); }
 
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream) {
-  TcParams p;
+  TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.cblocks = g.cp / bk;
   p.ksub = pick_ksub(bk, p.cblocks);
@@ -739,17 +844,56 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   return launch_bk<1>(bk, bn, tmA, tmB, p, stream);
 }
 
-int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
-                 const EpiParams& ep, cudaStream_t stream) {
-  TcParams p;
+// Tile width and K split for an fc shape. Large M: one wide tile per CTA. Small M (a weight
+// stream): every SM should pull an equal, minimal share of bytes through its ~43 B/clk L2
+// port, so pick the (BN, splits) pair with the fewest bytes per CTA, counting the activation
+// rows each N tile re-reads and the s32 partials it writes and the reduce kernel re-reads.
+void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_per_out) {
+  const int num_kb = (k + 127) / 128;
+  const int tiles_m = (m + BM - 1) / BM;
+  int bn = pick_bn(ldy);
+  int splits = 1, kb_per = num_kb;
+  const bool allow = std::getenv("I8IE_NO_SPLITK") == nullptr && std::getenv("I8IE_TC_BN") == nullptr;
+  if (allow && tiles_m * ((ldy + bn - 1) / bn) * 2 <= num_sms() && num_kb >= 2) {
+    long long best = -1;
+    const int rows = m < BM ? m : BM;
+    for (int cand : {256, 192, 128, 96, 64, 32}) {
+      if (cand > bn && cand > ((ldy + 31) / 32) * 32) continue;
+      const int tiles = tiles_m * ((ldy + cand - 1) / cand);
+      if (tiles > num_sms()) continue;
+      int s = num_sms() / tiles;
+      if (s > num_kb) s = num_kb;
+      if (s > 32) s = 32;
+      const int per = (num_kb + s - 1) / s;
+      s = (num_kb + per - 1) / per;
+      const long long cost = (long long)per * 128 * (rows + cand) + (s > 1 ? 8ll * rows * cand : 0);
+      if (best < 0 || cost < best) { best = cost; bn = cand; splits = s; kb_per = per; }
+    }
+  }
+  *bn_out = bn; *splits_out = splits; *kb_per_out = kb_per;
+}
+
+int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
+                 int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream) {
+  TcParams p{};
   p.M = m; p.N = n; p.out_cp = ldy;
   p.cblocks = 1; p.ksub = 1; p.num_kb = (k + 127) / 128;
   p.kh = p.kw = 1; p.stride_h = p.stride_w = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
-  return launch_bk<0>(128, bn, tmA, tmB, p, stream);
+  if (splits <= 1) return launch_bk<0>(128, bn, tmA, tmB, p, stream);
+  // split K across CTAs, then fold the partial sums (exact: integer adds commute)
+  p.splits = splits; p.kb_per = kb_per;
+  p.ws_ld = ((ldy + bn - 1) / bn) * bn;
+  int rc = ensure_workspace(sizeof(int32_t) * (size_t)p.splits * m * p.ws_ld, stream, &p.ws);
+  if (rc != I8IE_OK) return rc;
+  rc = launch_bk<0>(128, bn, tmA, tmB, p, stream);
+  if (rc != I8IE_OK) return rc;
+  const long long threads = (long long)m * (ldy / 4);
+  fc_splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(p.ws, p.splits, m, n, p.ws_ld, ldy, y,
+                                                                              ep, p.fast_requant);
+  return check_launch("fc_splitk_reduce_kernel");
 }
-
 
 // ---- stem path host side ---------------------------------------------------------------------
 bool tc_stem_eligible(const GemmGeom& g, int c) {
@@ -810,7 +954,7 @@ int tc_encode_stem_act_map(CUtensorMap* tm, const uint8_t* xs, const GemmGeom& g
 
 int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
                    const EpiParams& ep, cudaStream_t stream) {
-  TcParams p;
+  TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.cblocks = 1; p.ksub = 1; p.num_kb = g.kh;
   p.kh = g.kh; p.kw = 1; p.stride_h = g.stride; p.stride_w = g.stride / 4; p.pad = 0;
