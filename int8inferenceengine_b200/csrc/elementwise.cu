@@ -244,10 +244,14 @@ __global__ void __launch_bounds__(kThreads) relu_flat_kernel(const uint8_t* __re
 
 // ---- A11 max_pool2d<u8>, NHWC --------------------------------------------------
 // One thread per (output pixel, 16-channel group): k*k 128-bit loads, byte-wise max.
+// KS > 0: window size known at compile time -> the k*k loads are all in flight before the
+// first max (the runtime-k loop serialises load -> max -> load and is latency-bound).
+template <int KS>
 __global__ void __launch_bounds__(kThreads) maxpool_nhwc_kernel(const uint8_t* __restrict__ x,
                                                                 uint8_t* __restrict__ y, int n, int h,
-                                                                int w, int c, int cp, int ks, int st,
+                                                                int w, int c, int cp, int ks_rt, int st,
                                                                 int oh, int ow, int out_nchw) {
+  const int ks = KS > 0 ? KS : ks_rt;
   const int groups = cp >> 4;
   const int64_t total = (int64_t)n * oh * ow * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -257,13 +261,26 @@ __global__ void __launch_bounds__(kThreads) maxpool_nhwc_kernel(const uint8_t* _
     const int ox = (int)(r % ow); r /= ow;
     const int oy = (int)(r % oh);
     const int img = (int)(r / oh);
+    const uint8_t* base = x + (((int64_t)img * h + oy * st) * w + ox * st) * cp + g * 16;
     uint4 m = make_uint4(0, 0, 0, 0);  // min<u8_t>() == 0 (functional.cc:33-35)
-    for (int a = 0; a < ks; ++a)
-      for (int b = 0; b < ks; ++b) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-            x + (((int64_t)img * h + (oy * st + a)) * w + (ox * st + b)) * cp + g * 16));
-        m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
+    if (KS > 0) {
+      uint4 v[KS > 0 ? KS * KS : 1];
+#pragma unroll
+      for (int a = 0; a < KS; ++a)
+#pragma unroll
+        for (int b = 0; b < KS; ++b)
+          v[a * KS + b] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)a * w + b) * cp));
+#pragma unroll
+      for (int i = 0; i < KS * KS; ++i) {
+        m.x = __vmaxu4(m.x, v[i].x); m.y = __vmaxu4(m.y, v[i].y); m.z = __vmaxu4(m.z, v[i].z); m.w = __vmaxu4(m.w, v[i].w);
       }
+    } else {
+      for (int a = 0; a < ks; ++a)
+        for (int b = 0; b < ks; ++b) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)a * w + b) * cp));
+          m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
+        }
+    }
     if (!out_nchw) {
       *reinterpret_cast<uint4*>(y + (((int64_t)img * oh + oy) * ow + ox) * cp + g * 16) = m;
     } else {
@@ -499,8 +516,13 @@ int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int 
   const int oh = (h - ksize) / stride + 1, ow = (w - ksize) / stride + 1;
   const int64_t items = (int64_t)n * oh * ow * (cp / 16);
   if (items == 0) return I8IE_OK;
-  maxpool_nhwc_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
+  const int grid = stream_grid(items, kThreads);
+  if (ksize == 3)
+    maxpool_nhwc_kernel<3><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
+  else if (ksize == 2)
+    maxpool_nhwc_kernel<2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
+  else
+    maxpool_nhwc_kernel<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
   return check_launch("maxpool_nhwc_kernel");
 }
 

@@ -48,6 +48,9 @@ struct TcParams {
   int splits, kb_per;
   int32_t* ws;                // [splits][M][ws_ld]
   int ws_ld;
+  // 128-row sub-tiles per CTA tile (1 or 2): two accumulators share every weight stage, which
+  // cuts the L2->SM bytes per MAC (the binding limit of a 128 x BN tile, ~43 B/clk/SM)
+  int mt;
 };
 
 namespace {
@@ -59,10 +62,13 @@ constexpr int kMaxStages = 16;
 
 template <int BN>
 constexpr uint32_t acc_stride() { return (BN + 31) / 32 * 32; }   // TMEM columns per accumulator buffer
+// accumulator ring in TMEM: as many BN-column buffers as fit in the 512 columns, at most 4
+template <int BN>
+constexpr uint32_t num_acc() { return 512 / acc_stride<BN>() >= 4 ? 4 : 512 / acc_stride<BN>(); }
 template <int BN>
 constexpr uint32_t tmem_cols() {
-  return 2 * acc_stride<BN>() <= 32 ? 32 : 2 * acc_stride<BN>() <= 64 ? 64 : 2 * acc_stride<BN>() <= 128 ? 128
-         : 2 * acc_stride<BN>() <= 256 ? 256 : 512;
+  return num_acc<BN>() * acc_stride<BN>() <= 32 ? 32 : num_acc<BN>() * acc_stride<BN>() <= 64 ? 64
+         : num_acc<BN>() * acc_stride<BN>() <= 128 ? 128 : num_acc<BN>() * acc_stride<BN>() <= 256 ? 256 : 512;
 }
 
 // control block placed after the operand ring
@@ -70,8 +76,8 @@ template <int BN>
 struct alignas(16) TcControl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[4];
+  uint64_t tmem_empty[4];
   uint32_t tmem_slot;
   uint32_t pad_[3];
   int32_t oc[2][BN];
@@ -79,7 +85,7 @@ struct alignas(16) TcControl {
 };
 
 template <int BN, int BK>
-__host__ __device__ constexpr int stage_bytes(int ksub) { return ksub * (BM * BK + BN * BK); }
+__host__ __device__ constexpr int stage_bytes(int ksub, int mt) { return ksub * (mt * BM * BK + BN * BK); }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
@@ -110,10 +116,14 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
       v[4 * g] += o.x; v[4 * g + 1] += o.y; v[4 * g + 2] += o.z; v[4 * g + 3] += o.w;
     }
     if (corr) {   // border pixels only: zero-fill -> zero-point padding correction
-      const int nmax = p.N - (n0 + c0);
+      // (table rows are padded to a multiple of 32 channels, so whole chunks are read as int4)
+      const int4* c4 = reinterpret_cast<const int4*>(corr + n0 + c0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nmax) v[j] = (uint32_t)((int32_t)v[j] + p.zp_in * __ldg(corr + n0 + c0 + j));
+      for (int g = 0; g < 8; ++g) {
+        const int4 t = __ldg(c4 + g);
+        v[4 * g] += (uint32_t)(p.zp_in * t.x); v[4 * g + 1] += (uint32_t)(p.zp_in * t.y);
+        v[4 * g + 2] += (uint32_t)(p.zp_in * t.z); v[4 * g + 3] += (uint32_t)(p.zp_in * t.w);
+      }
     }
     if (has_bias) {   // fully_connected.cc:44
 #pragma unroll
@@ -166,14 +176,16 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
 
 // Persistent, warp-specialised implicit GEMM. MODE 0: A rows via a 2-D tiled map (fc);
 // MODE 1: A gathered by the TMA im2col engine (conv, incl. the stem view).
-template <int BN, int BK, int MODE>
+template <int BN, int BK, int MODE, int MT>
 __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kSubA = BM * BK, kSubB = BN * BK;
-  const int kStage = p.ksub * (kSubA + kSubB);
+  constexpr uint32_t NACC = num_acc<BN>();
+  constexpr int mt = MT;
+  const int kStage = p.ksub * (mt * kSubA + kSubB);   // [ksub][mt] A sub-blocks, then [ksub] B sub-blocks
   TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       ptx::mbar_init(&ctl->full[s], 1);
       ptx::mbar_init(&ctl->empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < (int)NACC; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
       ptx::mbar_init(&ctl->tmem_empty[b], kEpiWarps);
     }
@@ -206,14 +218,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       bool alive = true;
       for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
         const int split = tile / mn_tiles, mn = tile % mn_tiles;
-        const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
+        const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
-        int bw = 0, bh = 0, bn = 0;
+        int bw[MT] = {}, bh[MT] = {}, bn[MT] = {};
         if (MODE == 1) {
-          const int q = m0 % p.ow, t = m0 / p.ow;
-          bw = q * p.stride_w - p.pad;
-          bh = (t % p.oh) * p.stride_h - p.pad;
-          bn = t / p.oh;
+#pragma unroll
+          for (int t = 0; t < mt; ++t) {
+            const int mm = m0 + t * BM;
+            const int q = mm % p.ow, r = mm / p.ow;
+            bw[t] = q * p.stride_w - p.pad;
+            bh[t] = (r % p.oh) * p.stride_h - p.pad;
+            bn[t] = r / p.oh;
+          }
         }
         int cb = 0, kx = 0, ky = 0;   // (split-K is only used with MODE 0, where these stay 0)
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -222,126 +238,144 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
           if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
           ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)kStage);
           uint8_t* sa = smem + (size_t)s * kStage;
-          uint8_t* sb = sa + p.ksub * kSubA;
+          uint8_t* sb = sa + p.ksub * mt * kSubA;
           for (int j = 0; j < p.ksub; ++j) {
             const int kidx = kb * p.ksub + j;   // BK-byte sub-block index along K
-            if (MODE == 1) {
-              ptx::tma_load_im2col_4d(sa + j * kSubA, &tmA, &ctl->full[s], cb * BK, bw, bh, bn, (uint16_t)kx, (uint16_t)ky);
-              if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
-            } else {
-              ptx::tma_load_2d(sa + j * kSubA, &tmA, &ctl->full[s], kidx * BK, m0);
+#pragma unroll
+            for (int t = 0; t < mt; ++t) {
+              uint8_t* dst = sa + (j * mt + t) * kSubA;
+              if (MODE == 1)
+                ptx::tma_load_im2col_4d(dst, &tmA, &ctl->full[s], cb * BK, bw[t], bh[t], bn[t], (uint16_t)kx, (uint16_t)ky);
+              else
+                ptx::tma_load_2d(dst, &tmA, &ctl->full[s], kidx * BK, m0 + t * BM);
             }
+            if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } } }
             ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread, accumulators ping-pong between two TMEM buffers =====
+    // ===== MMA issuer: one thread; accumulators rotate through the TMEM ring =====
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
-      uint32_t it = 0, tcount = 0;
+      const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
+      uint32_t it = 0, acc_it = 0;
       bool alive = true;
-      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++tcount) {
-        const uint32_t buf = tcount & 1, bph = (tcount >> 1) & 1;
-        if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
+      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, acc_it += mt) {
+        uint32_t d_tmem[MT];
+#pragma unroll
+        for (int t = 0; t < mt; ++t) {
+          const uint32_t slot = (acc_it + t) % NACC, sph = ((acc_it + t) / NACC) & 1;
+          if (alive && !ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; }
+          d_tmem[t] = tmem_base + slot * acc_stride<BN>();
+        }
+        if (!alive) break;
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * acc_stride<BN>();
         const int kb0 = (tile / mn_tiles) * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+        uint32_t accf = 0;   // the first MMA of a tile overwrites the accumulator
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
-          const uint32_t sb = sa + p.ksub * kSubA;
+          // descriptor low words; every further operand is a constant (>>4) offset away
+          uint32_t a_lo = ptx::smem_desc_lo(sa);
+          uint32_t b_lo = ptx::smem_desc_lo(sa + p.ksub * mt * kSubA);
           for (int j = 0; j < p.ksub; ++j) {
 #pragma unroll
             for (int k = 0; k < BK / 32; ++k) {
-              ptx::mma_i8_ss(d_tmem, ptx::make_smem_desc<BK>(sa + j * kSubA + k * 32),
-                             ptx::make_smem_desc<BK>(sb + j * kSubB + k * 32), idesc, ((kb - kb0) | j | k) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int t = 0; t < mt; ++t)
+                ptx::mma_i8_ss_lohi(d_tmem[t], a_lo + (uint32_t)((t * kSubA + k * 32) >> 4), desc_hi,
+                                    b_lo + (uint32_t)((k * 32) >> 4), desc_hi, idesc, accf);
+              accf = 1;
             }
+            a_lo += (uint32_t)((mt * kSubA) >> 4);
+            b_lo += (uint32_t)(kSubB >> 4);
           }
           ptx::tc_commit(&ctl->empty[s]);   // slot reusable once these MMAs have read it
         }
-        if (alive) ptx::tc_commit(&ctl->tmem_full[buf]);
+        if (alive) {
+#pragma unroll
+          for (int t = 0; t < mt; ++t) ptx::tc_commit(&ctl->tmem_full[(acc_it + t) % NACC]);
+        }
       }
-      if (!alive) {   // unblock the epilogue so that the CTA can exit
-        ptx::mbar_arrive(&ctl->tmem_full[0]);
-        ptx::mbar_arrive(&ctl->tmem_full[1]);
-      }
+      if (!alive)   // unblock the epilogue so that the CTA can exit
+        for (int b = 0; b < (int)NACC; ++b) ptx::mbar_arrive(&ctl->tmem_full[b]);
     }
   } else {
     // ===== epilogue: 8 warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
     const int quad = warp & 3;
-    const int et = threadIdx.x - 64;   // 0..127
+    const int et = threadIdx.x - 64;
     const float rcp = __frcp_rn(p.ep.sc);
     const bool has_bias = p.ep.bias_f != nullptr;
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1, bph = (tcount >> 1) & 1;
+    uint32_t tcount = 0, acc_it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount, acc_it += mt) {
+      const uint32_t ob = tcount & 1;
       const int split = tile / mn_tiles, mn = tile % mn_tiles;
-      const int m0 = (mn / p.tiles_n) * BM, n0 = (mn % p.tiles_n) * BN;
-      if (p.splits > 1) {
-        // split-K: dump the raw partial accumulators; fc_splitk_reduce_kernel finishes the job
-        const int m = m0 + quad * 32 + lane;
-        const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
-        if (!ok) atomicCAS(&g_tc_error, 0, 3);
-        ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
-        int32_t* wrow = p.ws + ((size_t)split * p.M + (m < p.M ? m : 0)) * p.ws_ld + n0;
-#pragma unroll 1
-        for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 64) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
-          ptx::tmem_ld_wait();
-          if (m < p.M && ok) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          }
+      const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
+      if (p.splits <= 1) {
+        // stage this tile's per-channel offsets (double-buffered: one barrier per tile)
+        for (int j = et; j < BN; j += 32 * kEpiWarps) {
+          const int n = n0 + j;
+          ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
+          ctl->bias[ob][j] = (n < p.N && has_bias) ? __ldg(p.ep.bias_f + n) : 0.f;
         }
+        epi_bar_sync();
+      }
+#pragma unroll 1
+      for (int t = 0; t < mt; ++t) {
+        const uint32_t slot = (acc_it + t) % NACC, sph = ((acc_it + t) / NACC) & 1;
+        const int m = m0 + t * BM + quad * 32 + lane;
+        const uint32_t t_row = tmem_base + slot * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
+        if (p.splits > 1) {
+          // split-K: dump the raw partial accumulators; fc_splitk_reduce_kernel finishes the job
+          const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
+          if (!ok) atomicCAS(&g_tc_error, 0, 3);
+          ptx::tc_fence_after();
+          int32_t* wrow = p.ws + ((size_t)split * p.M + (m < p.M ? m : 0)) * p.ws_ld + n0;
+#pragma unroll 1
+          for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 64) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
+            ptx::tmem_ld_wait();
+            if (m < p.M && ok) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+          }
+        } else {
+          // spatial border class of this output pixel -> row of the zero-point correction table
+          const int32_t* corr = nullptr;
+          if (MODE == 1 && p.border_tab && m < p.M) {
+            const int q = m % p.ow, pr = (m / p.ow) % p.oh;
+            const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
+            const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
+            const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
+            const int d = p.pad + 1;
+            const int cls = ((th * d + bh) * d + tw) * d + bw;
+            if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
+          }
+          const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
+          if (!ok) atomicCAS(&g_tc_error, 0, 3);
+          ptx::tc_fence_after();
+          epilogue_row<BN>(p, t_row, (m < p.M && ok) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
+                           ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
+        }
+        // hand the accumulator buffer back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
-        continue;
+        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[slot]);
       }
-      // stage this tile's per-channel offsets (double-buffered: one barrier per tile)
-      for (int j = et; j < BN; j += 32 * kEpiWarps) {
-        const int n = n0 + j;
-        ctl->oc[buf][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
-        ctl->bias[buf][j] = (n < p.N && has_bias) ? __ldg(p.ep.bias_f + n) : 0.f;
-      }
-      epi_bar_sync();
-      const int m = m0 + quad * 32 + lane;
-      // spatial border class of this output pixel -> row of the zero-point correction table
-      const int32_t* corr = nullptr;
-      if (MODE == 1 && p.border_tab && m < p.M) {
-        const int q = m % p.ow, pr = (m / p.ow) % p.oh;
-        const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
-        const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
-        const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
-        const int d = p.pad + 1;
-        const int cls = ((th * d + bh) * d + tw) * d + bw;
-        if (cls != 0) corr = p.border_tab + (size_t)cls * p.N;
-      }
-      const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
-      if (!ok) atomicCAS(&g_tc_error, 0, 3);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
-      epilogue_row<BN>(p, t_row, (m < p.M && ok) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[buf]),
-                       ptx::smem_u32(ctl->bias[buf]), corr, rcp, (warp - 2) >> 2);
-      // hand the accumulator buffer back to the MMA warp
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
 }
-
 
 // ---- stem2: smem-resident stem rows, sliding windows expressed by overlapping descriptors ---
 // For stride-4 stems the window of output pixel q starts at superpixel q, i.e. 16 bytes after
@@ -491,21 +525,23 @@ __global__ void border_table_kernel(const int8_t* __restrict__ wp, int32_t* __re
                                     int kw, int cp, int pad) {
   const int d = pad + 1;
   const int ncls = d * d * d * d;
+  const int npitch = (N + 31) & ~31;   // rows padded to 32 channels (zeros) for 128-bit lookups
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= ncls * N) return;
-  const int n = idx % N, cls = idx / N;
+  if (idx >= ncls * npitch) return;
+  const int n = idx % npitch, cls = idx / npitch;
   const int bw = cls % d, tw = (cls / d) % d, bh = (cls / (d * d)) % d, th = cls / (d * d * d);
   int32_t s = 0;
-  for (int r = 0; r < kh; ++r)
-    for (int c = 0; c < kw; ++c) {
-      const bool inb = (r >= th) && (r < kh - bh) && (c >= tw) && (c < kw - bw);
-      if (inb) continue;
-      const int8_t* w = wp + (((size_t)n * kh + r) * kw + c) * cp;
-      for (int ch = 0; ch < cp; ++ch) s += w[ch];
-    }
+  if (n < N) {
+    for (int r = 0; r < kh; ++r)
+      for (int c = 0; c < kw; ++c) {
+        const bool inb = (r >= th) && (r < kh - bh) && (c >= tw) && (c < kw - bw);
+        if (inb) continue;
+        const int8_t* w = wp + (((size_t)n * kh + r) * kw + c) * cp;
+        for (int ch = 0; ch < cp; ++ch) s += w[ch];
+      }
+  }
   tab[idx] = s;
 }
-
 
 // ---- stem path: small-C strided first-layer convs (AlexNet conv1: C=3, k=11, s=4, p=2) ------
 // A 3-channel NHWC image gives TMA/UMMA nothing to chew on (K blocks must be >= 32 bytes).
@@ -709,11 +745,35 @@ int encode_im2col_4d(CUtensorMap* tm, const void* base, const GemmGeom& g, int b
   return I8IE_OK;
 }
 
+template <int BN, int BK, int MODE, int MT>
+int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int smem, cudaStream_t stream) {
+  static int attr_smem = 0;
+  auto kern = tc_igemm_kernel<BN, BK, MODE, MT>;
+  if (attr_smem < smem) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  return check_launch("tc_igemm_kernel");
+}
+
 template <int BN, int BK, int MODE>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
   constexpr int kMaxSmem = 227 * 1024;
+  constexpr bool kHasMT2 = (MODE == 1 && BN >= 128);   // 256-row CTA tiles: conv with wide N tiles only
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
-  const int kStage = stage_bytes<BN, BK>(p.ksub);
+  if (p.mt < 1 || !kHasMT2) p.mt = 1;
+  if (p.mt == 2) {
+    // two 128-row sub-tiles only pay off when the wave count stays healthy and 3+ stages fit
+    const int tiles2 = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.out_cp + BN - 1) / BN);
+    const bool fits = (kMaxSmem - 1024 - ctl_bytes) / stage_bytes<BN, BK>(p.ksub, 2) >= 3;
+    // measured on B200: the lost epilogue/main-loop overlap (both accumulators busy) costs more
+    // than the saved weight traffic except in a few wave-quantisation cases -> opt-in only
+    if (!fits || tiles2 * 100 < num_sms() * 85 || std::getenv("I8IE_TC_MT2") == nullptr) p.mt = 1;
+  }
+  const int kStage = stage_bytes<BN, BK>(p.ksub, p.mt);
   int stages = (kMaxSmem - 1024 - ctl_bytes) / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (const char* e = std::getenv("I8IE_TC_STAGES")) {
@@ -723,19 +783,13 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaS
   I8IE_REQUIRE(stages >= 2, "tcgen05: stage of %d bytes leaves no room for a pipeline", kStage);
   p.stages = stages;
   const int smem = stages * kStage + ctl_bytes + 1024;
-  static int attr_smem = 0;
-  auto kern = tc_igemm_kernel<BN, BK, MODE>;
-  if (attr_smem < smem) {
-    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
-  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_m = (p.M + BM * p.mt - 1) / (BM * p.mt);
   p.tiles_n = (p.out_cp + BN - 1) / BN;
   if (p.splits < 1) { p.splits = 1; p.kb_per = p.num_kb; }
-  const int tiles = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
-  return check_launch("tc_igemm_kernel");
+  if constexpr (kHasMT2) {
+    if (p.mt == 2) return launch_kernel<BN, BK, MODE, 2>(tmA, tmB, p, smem, stream);
+  }
+  return launch_kernel<BN, BK, MODE, 1>(tmA, tmB, p, smem, stream);
 }
 
 template <int BK, int MODE>
@@ -807,7 +861,7 @@ int tc_conv_bk(const GemmGeom& g) { return g.cp % 128 == 0 ? 128 : g.cp % 64 == 
 int tc_border_table_size(const GemmGeom& g) {
   if (g.pad == 0) return 0;
   const int d = g.pad + 1;
-  return d * d * d * d * g.N;
+  return d * d * d * d * ((g.N + 31) & ~31);
 }
 
 int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* tab, cudaStream_t stream) {
@@ -841,6 +895,7 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  p.mt = 2;   // launch_cfg falls back to 1 when the shape is too small for it
   return launch_bk<1>(bk, bn, tmA, tmB, p, stream);
 }
 

@@ -108,6 +108,19 @@ __device__ __forceinline__ void mma_i8_ss(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors passed as (lo, hi) register pairs: the issuing thread only bumps
+// the 32-bit low words (start address field) between MMAs, no 64-bit ALU work in the loop.
+__device__ __forceinline__ void mma_i8_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -147,6 +160,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= layout << 61;
   return d;
 }
+
+// (lo, hi) halves of make_smem_desc<SW>: lo carries the start address (>>4) and LBO = 1
+template <int SW>
+__device__ __forceinline__ uint32_t smem_desc_hi() {
+  constexpr uint32_t layout = (SW == 128) ? 2 : (SW == 64) ? 4 : 6;
+  return (uint32_t)((SW * 8) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
 
 // No-swizzle K-major operand: core matrices of 8 rows x 16 bytes with rows 16 bytes apart;
 // `lbo` = byte distance between the two 16-byte K chunks of one MMA, `sbo` = between 8-row groups.
