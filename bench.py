@@ -275,11 +275,15 @@ def run_ours(args):
     glaunch0 = model.graph_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active = True
+    if args.profiler_range:      # ncu --profile-from-start off: capture exactly the timed steps
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     sync_all()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     sampler.active = False
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0 + model.graph_launches() - glaunch0
@@ -468,6 +472,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="global batch (default 100 at N=1, 1000 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

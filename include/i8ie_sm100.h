@@ -64,6 +64,18 @@ I8IE_API int i8ie_quantize_f32_u8(const float* x, uint8_t* q, int64_t n, float s
 I8IE_API int i8ie_quantize_nchw_f32_nhwc_u8(const float* x, uint8_t* q, int n, int c, int h, int w, int cp,
                                    float scale, int zp, void* stream);
 
+/* "_indirect" variants: identical arithmetic, but the SOURCE ADDRESS is read from device memory
+ * (*x_slot) when the kernel runs. A forward captured once into a CUDA graph can then be replayed
+ * on any input buffer by writing its address into the slot (stream-ordered) — no staging copy.
+ * The address stored in the slot must be 16-byte aligned. (No reference counterpart: the
+ * reference passes the Tensor by reference, module.py:20.) */
+I8IE_API int i8ie_quantize_f32_u8_indirect(const float* const* x_slot, uint8_t* q, int64_t n, float scale, int zp,
+                                  void* stream);
+I8IE_API int i8ie_quantize_nchw_f32_nhwc_u8_indirect(const float* const* x_slot, uint8_t* q, int n, int c, int h,
+                                            int w, int cp, float scale, int zp, void* stream);
+/* dst[0, nbytes) = (*src_slot)[0, nbytes); nbytes % 16 == 0, both 16-byte aligned. */
+I8IE_API int i8ie_copy_indirect(const void* const* src_slot, void* dst, int64_t nbytes, void* stream);
+
 /* A5: dequantize(float*, u8*, size, scale, zp), quantize_utils.cc:38-42:
  *   x[i] = (float)((int)q[i] - zp) * scale. Flat, dense. */
 I8IE_API int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, int zp, void* stream);
@@ -153,6 +165,11 @@ I8IE_API int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, 
 I8IE_API int i8ie_conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, float in_scale, int in_zp, uint8_t* y,
                        const int32_t* oc, float sb, float sc, int zp_out, int flags, int32_t* acc_out,
                        void* stream);
+
+/* Same with the image address read from *x_slot at run time (see the "_indirect" note above). */
+I8IE_API int i8ie_conv2d_f32_u8_indirect(i8ie_conv_plan* plan, const float* const* x_slot, float in_scale,
+                                int in_zp, uint8_t* y, const int32_t* oc, float sb, float sc, int zp_out,
+                                int flags, int32_t* acc_out, void* stream);
 
 /* Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52:
  *   acc = x[m,k] * w[n,k]^T + oc[n];  acc = (int)((float)acc + bias_f[n]);  y = requant(acc) [+relu]

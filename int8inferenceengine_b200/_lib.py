@@ -17,6 +17,8 @@ SYMBOLS = [
     "i8ie_u8_nchw_to_nhwc", "i8ie_u8_nhwc_to_nchw", "i8ie_quantize_weight_host", "i8ie_zp_offsets",
     "i8ie_pack_conv_weight", "i8ie_conv2d_plan_create", "i8ie_conv2d_plan_destroy",
     "i8ie_conv2d_plan_impl", "i8ie_conv2d_u8", "i8ie_conv2d_f32_u8", "i8ie_fc_u8", "i8ie_debug_tc_error",
+    "i8ie_quantize_f32_u8_indirect", "i8ie_quantize_nchw_f32_nhwc_u8_indirect", "i8ie_copy_indirect",
+    "i8ie_conv2d_f32_u8_indirect",
 ]
 
 _lib = None
@@ -67,6 +69,10 @@ def load():
     L.i8ie_conv2d_u8.argtypes = [vp, vp, vp, vp, f, f, f, i, i, i, vp, vp]
     L.i8ie_fc_u8.argtypes = [vp, i, vp, i, i, vp, i, i, i, i, vp, vp, f, f, f, i, i, vp, i, vp]
     L.i8ie_conv2d_f32_u8.argtypes = [vp, vp, f, i, vp, vp, f, f, i, i, vp, vp]
+    L.i8ie_conv2d_f32_u8_indirect.argtypes = [vp, vp, f, i, vp, vp, f, f, i, i, vp, vp]
+    L.i8ie_quantize_f32_u8_indirect.argtypes = [vp, vp, i64, f, i, vp]
+    L.i8ie_quantize_nchw_f32_nhwc_u8_indirect.argtypes = [vp, vp, i, i, i, i, i, f, i, vp]
+    L.i8ie_copy_indirect.argtypes = [vp, vp, i64, vp]
     L.i8ie_debug_tc_error.argtypes = [i]
     _lib = L
     return L

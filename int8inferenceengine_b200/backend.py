@@ -77,6 +77,42 @@ class _Storage:
         self.views = 0
 
 
+class _SlotStorage:
+    """Storage of a CUDA-graph input: the graph's first kernel reads the source ADDRESS from a
+    device slot at run time (the "_indirect" entry points), so a replay works on whatever buffer
+    the caller passed without a staging copy. Any consumer that needs the bytes at a fixed
+    address gets them materialised into a static buffer by one in-graph copy kernel."""
+
+    def __init__(self, slot, numel, device):
+        self.slot, self.numel, self.device = slot, int(numel), device
+        self.views = 0
+        self._static = None
+
+    @property
+    def materialised(self):
+        return self._static is not None
+
+    @property
+    def t(self):
+        if self._static is None:
+            L = _need_cuda()
+            self._static = torch.empty(self.numel, dtype=torch.float32, device=self.device)
+            if (self.numel * 4) % 16 == 0:
+                check(L.i8ie_copy_indirect(self.slot.data_ptr(), self._static.data_ptr(), self.numel * 4, _stream()),
+                      "copy_indirect")
+            else:
+                raise I8ieError("graph input of %d floats is not a multiple of 16 bytes" % self.numel)
+        return self._static
+
+
+def _src_ptrs(x):
+    """(direct pointer or None, slot pointer or None, device) of a float tensor's bytes."""
+    st = x._st
+    if isinstance(st, _SlotStorage) and not st.materialised:
+        return None, st.slot.data_ptr(), st.device
+    return st.t.data_ptr(), None, st.t.device
+
+
 class _TensorBase:
     torch_dtype = None
     np_dtype = None
@@ -292,9 +328,14 @@ class _DeferredQuant:
     def launch(self):
         L = _need_cuda()
         n, c, h, w, cp = self.geom
-        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=self.src.buf.device)
-        check(L.i8ie_quantize_nchw_f32_nhwc_u8(self.src.buf.data_ptr(), out.data_ptr(), n, c, h, w, cp,
-                                               self.scale, self.zp, _stream()), "quantize_nchw_f32_nhwc_u8")
+        ptr, slot, dev = _src_ptrs(self.src)
+        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=dev)
+        if slot is not None:
+            check(L.i8ie_quantize_nchw_f32_nhwc_u8_indirect(slot, out.data_ptr(), n, c, h, w, cp, self.scale,
+                                                            self.zp, _stream()), "quantize_nchw_f32_nhwc_u8_indirect")
+        else:
+            check(L.i8ie_quantize_nchw_f32_nhwc_u8(ptr, out.data_ptr(), n, c, h, w, cp, self.scale, self.zp,
+                                                   _stream()), "quantize_nchw_f32_nhwc_u8")
         return _Storage(out), "nhwc", self.geom
 
 
@@ -334,16 +375,20 @@ def quantize(x, scale, zero_point):
     if not 0 <= zp <= 255:
         raise TypeError("quantize(): zero_point must fit unsigned char")
     scale = float(np.float32(scale))
-    src = x.buf
     shp = x._shape
     if len(shp) in (2, 4):
         n, c = shp[0], shp[1]
         h, w = (shp[2], shp[3]) if len(shp) == 4 else (1, 1)
         geom = (n, c, h, w, _act_pitch(c))
         return TensorU8(None, shp, "nhwc", geom, scale, zp, deferred=_DeferredQuant(x, scale, zp, geom))
-    out = torch.empty(src.numel(), dtype=torch.uint8, device=src.device)
-    check(L.i8ie_quantize_f32_u8(src.data_ptr(), out.data_ptr(), src.numel(), scale, zp, _stream()),
-          "quantize_f32_u8")
+    ptr, slot, dev = _src_ptrs(x)
+    numel = int(np.prod(shp)) if shp else 1
+    out = torch.empty(numel, dtype=torch.uint8, device=dev)
+    if slot is not None:
+        check(L.i8ie_quantize_f32_u8_indirect(slot, out.data_ptr(), numel, scale, zp, _stream()),
+              "quantize_f32_u8_indirect")
+    else:
+        check(L.i8ie_quantize_f32_u8(ptr, out.data_ptr(), numel, scale, zp, _stream()), "quantize_f32_u8")
     return TensorU8(_Storage(out), shp, "dense", None, scale, zp)
 
 
@@ -755,11 +800,13 @@ class Conv2d(_BaseLayer):
         ow = (w - kw + 2 * self._pad) // self._stride + 1
         oc, _ = self._offsets(int(in_zp), in_scale, True)
         out_cp = _act_pitch(kc)
-        out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=x.buf.device)
+        ptr, slot, dev = _src_ptrs(x)
+        out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=dev)
         flags = 1 if (self.fuse_relu if relu is None else relu) else 0
-        check(L.i8ie_conv2d_f32_u8(plan, x.buf.data_ptr(), in_scale, int(in_zp), out.data_ptr(), oc.data_ptr(),
-                                   float(self._w_scale), float(self._scale), self._zp, flags,
-                                   acc_out.data_ptr() if acc_out is not None else None, _stream()),
+        fn = L.i8ie_conv2d_f32_u8_indirect if slot is not None else L.i8ie_conv2d_f32_u8
+        check(fn(plan, slot if slot is not None else ptr, in_scale, int(in_zp), out.data_ptr(), oc.data_ptr(),
+                 float(self._w_scale), float(self._scale), self._zp, flags,
+                 acc_out.data_ptr() if acc_out is not None else None, _stream()),
               "conv2d_f32_u8")
         self._last_impl = 3
         return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
@@ -772,27 +819,33 @@ def graphable(x):
 
 
 def capture_forward(fn, x):
-    """Captures fn(Tensor(static copy of x)) into a CUDA graph. The warm-up calls before this
-    have already created every plan / offset table / packed weight, so nothing allocates
-    through the C ABI or synchronises while the stream is capturing."""
+    """Captures fn(graph-input tensor) into a CUDA graph. The warm-up calls before this have
+    already created every plan / offset table / packed weight, so nothing allocates through the
+    C ABI or synchronises while the stream is capturing. The input is addressed through a device
+    slot (_SlotStorage), so replays read the caller's buffer in place."""
     from .api import Tensor
-    static_in = torch.empty_like(x.buf)
-    static_in.copy_(x.buf)
+    dev = x.buf.device
+    slot = torch.zeros(2, dtype=torch.int64, device=dev)   # 16-byte slot; [0] = source address
+    keep = x.buf if x.buf.data_ptr() % 16 == 0 else x.buf.clone()
+    slot[0] = keep.data_ptr()
     torch.cuda.synchronize()
     before = _lib.launch_count()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        out = fn(Tensor(TensorF32(_Storage(static_in), x._shape)))
+        out = fn(Tensor(TensorF32(_SlotStorage(slot, x.buf.numel(), dev), x._shape)))
         out_buf = out.data.buf
     kernels = _lib.launch_count() - before
     if not isinstance(out.data, TensorF32):
         raise RuntimeError("forward() did not return a dequantised tensor")
-    return {"graph": g, "static_in": static_in, "out_buf": out_buf, "out_shape": list(out.data._shape),
+    return {"graph": g, "slot": slot, "out_buf": out_buf, "out_shape": list(out.data._shape),
             "kernels": int(kernels), "replays": 0}
 
 
 def replay_forward(st, x):
-    st["static_in"].copy_(x.buf, non_blocking=True)
+    src = x.buf
+    if src.data_ptr() % 16 != 0:
+        src = src.clone()
+    st["slot"][:1].fill_(src.data_ptr())      # stream-ordered: the value travels as a kernel argument
     st["graph"].replay()
     st["replays"] += 1
     return TensorF32(_Storage(st["out_buf"].clone()), st["out_shape"])

@@ -67,13 +67,20 @@ __device__ __forceinline__ uint32_t requant_u8(int32_t acc, float sa, float sb, 
   return (quant >= 255.f) ? 255u : (quant < 0.f) ? 0u : (uint32_t)__float2int_rz(quant);
 }
 
+// (r >= 255) ? 255 : (r < 0) ? 0 : (u8)trunc(r), NaN -> 0: one saturating convert (F2IP.U8.F32.TRUNC)
+__device__ __forceinline__ uint32_t f32_to_u8_sat_rz(float r) {
+  uint32_t y;
+  asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(y) : "f"(r));
+  return y;
+}
+
 // Same result as requant_u8 with the IEEE division d / sc replaced by the classic
 // FMA-corrected quotient (rcp = RN(1/sc) hoisted out of the loop):
 //   q0 = RN(d*rcp); e = RN(d - sc*q0) (exact); q = RN(q0 + e*rcp) == RN(d / sc)
 // (Markstein's theorem: correctly rounded when rcp is the correctly rounded reciprocal, q0
 // is faithful and nothing over/underflows — the host only selects this path when sc, sa*sb
-// and the reachable |d| sit well inside the normal range, see requant_fast_ok()). The clamp
-// is done in fp32 before the truncating convert: identical to the reference's
+// and the reachable |d| sit well inside the normal range, see requant_fast_ok()). Clamp and
+// truncation are one saturating convert: identical to the reference's
 // (q >= 255) ? 255 : (q < 0) ? 0 : (u8)q for every input incl. NaN -> 0.
 __device__ __forceinline__ uint32_t requant_u8_fast(int32_t acc, float sa, float sb, float sc, float rcp,
                                                     float zp_c) {
@@ -81,8 +88,64 @@ __device__ __forceinline__ uint32_t requant_u8_fast(int32_t acc, float sa, float
   const float q0 = __fmul_rn(d, rcp);
   const float e = __fmaf_rn(-sc, q0, d);
   const float q = __fmaf_rn(e, rcp, q0);
-  const float r = fminf(fmaxf(__fadd_rn(q, zp_c), 0.f), 255.f);
-  return __float2uint_rz(r);
+  return f32_to_u8_sat_rz(__fadd_rn(q, zp_c));
+}
+
+// ---- packed fp32x2 arithmetic (sm_100a FMUL2 / FFMA2 / FADD2) -------------------------------
+// Two IEEE round-to-nearest fp32 operations per issued instruction; each half rounds exactly
+// like the scalar __fmul_rn / __fmaf_rn / __fadd_rn, so results are bit-identical.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// Constants of the fast requantise, broadcast into both halves once per thread.
+struct RequantFast2 {
+  f32x2_t sa, sb, rcp, nsc, zp;
+  float zpf;
+};
+__device__ __forceinline__ RequantFast2 make_requant_fast2(float sa, float sb, float sc, float rcp, float zpf) {
+  RequantFast2 c;
+  c.sa = f2_pack(sa, sa); c.sb = f2_pack(sb, sb); c.rcp = f2_pack(rcp, rcp); c.nsc = f2_pack(-sc, -sc);
+  c.zp = f2_pack(zpf, zpf);
+  c.zpf = zpf;
+  return c;
+}
+// Two accumulators -> two u8 codes (same value as requant_u8_fast, then max(y, zp) if relu: the
+// relu<u8> of functional.cc:22-23 is max(r, zp) before the monotone truncating convert).
+template <bool RELU>
+__device__ __forceinline__ void requant2_u8_fast(int32_t a0, int32_t a1, const RequantFast2& c, uint32_t& y0,
+                                                 uint32_t& y1) {
+  f32x2_t d = f2_pack(__int2float_rn(a0), __int2float_rn(a1));
+  d = f2_mul(f2_mul(d, c.sa), c.sb);
+  const f32x2_t q0 = f2_mul(d, c.rcp);
+  const f32x2_t e = f2_fma(c.nsc, q0, d);
+  const f32x2_t q = f2_fma(e, c.rcp, q0);
+  float r0, r1;
+  f2_unpack(f2_add(q, c.zp), r0, r1);
+  if (RELU) { r0 = fmaxf(r0, c.zpf); r1 = fmaxf(r1, c.zpf); }
+  y0 = f32_to_u8_sat_rz(r0);
+  y1 = f32_to_u8_sat_rz(r1);
 }
 
 // FC's `C[i*n+j] += q_bias[j] / in.scale()` (fully_connected.cc:44): int += float.
@@ -91,8 +154,26 @@ __device__ __forceinline__ int32_t fc_bias_add(int32_t acc, float bias_f) {
 }
 
 // A1 quantize element (quantize_utils.cc:49): (u8)(x/scale + zp), unclamped.
+// The cast is x86's cvttss2si to int32, then the low byte: anything outside the int32 range
+// (and NaN) converts to 0x80000000 -> byte 0. CUDA's convert saturates positive overflow to
+// 0x7fffffff instead, so that case is mapped explicitly.
+__device__ __forceinline__ uint32_t f2u8_wrap_x86(float v) {
+  return (v >= 2147483648.f) ? 0u : ((uint32_t)__float2int_rz(v) & 0xffu);
+}
 __device__ __forceinline__ uint32_t quant_u8_wrap(float x, float scale, float zpf) {
-  return (uint32_t)__float2int_rz(__fadd_rn(__fdiv_rn(x, scale), zpf)) & 0xffu;
+  return f2u8_wrap_x86(__fadd_rn(__fdiv_rn(x, scale), zpf));
+}
+// Same result with x / scale computed as the FMA-corrected product with rcp = RN(1/scale)
+// (Markstein, as in requant_u8_fast; the host selects this path only for a mid-range scale,
+// see quant_fast_ok). Elements too large for the intermediates (|x| >= 1e18, inf, NaN) take
+// the IEEE division; tiny ones give |quotient| < 2^-30 either way, which cannot change
+// trunc(quotient + zp).
+__device__ __forceinline__ uint32_t quant_u8_wrap_fast(float x, float scale, float rcp, float zpf) {
+  const float q0 = __fmul_rn(x, rcp);
+  const float e = __fmaf_rn(-scale, q0, x);
+  float q = __fmaf_rn(e, rcp, q0);
+  if (!(fabsf(x) < 1e18f)) q = __fdiv_rn(x, scale);
+  return f2u8_wrap_x86(__fadd_rn(q, zpf));
 }
 
 // A5 dequantize element (quantize_utils.cc:40).
@@ -121,6 +202,14 @@ __device__ __forceinline__ float4 ld_stream_f4(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)
@@ -143,6 +232,14 @@ inline bool requant_fast_ok(float sa, float sb, float sc) {
   const double dmax = 2147483648.0 * (double)sa * (double)sb;
   const double dmin = (double)sa * (double)sb;
   return dmax < 1e30 && dmin > 1e-30 && dmax / sc < 1e30 && dmin / sc > 1e-30;
+}
+
+// Host-side guard for quant_u8_wrap_fast.
+inline bool quant_fast_ok(float scale) {
+  if (!(scale > 1e-18f && scale < 1e18f)) return false;
+  uint32_t bits;
+  memcpy(&bits, &scale, sizeof(bits));
+  return (bits & 0x7fffffu) != 0x7fffffu;
 }
 
 // epilogue parameters shared by the SIMT and tcgen05 GEMM-shaped kernels

@@ -33,30 +33,49 @@ inline int stream_grid(int64_t work_items, int per_block) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
 
 // ---- A1 quantize f32 -> u8 (flat) -------------------------------------------
-// 16 elements per thread-iteration: 4 x 128-bit loads in flight, one 128-bit store.
+// Warp-coalesced streaming: each thread issues kU independent 128-bit loads, the j-th one of
+// a warp covering one contiguous 512-byte run, and writes one 32-bit word per load (128 B
+// per warp-store). FAST: the IEEE division x / scale is the FMA-corrected product with the
+// hoisted reciprocal (exactly RN(x / scale), see quant_u8_wrap_fast) — no MUFU per element.
+constexpr int kU = 4;
+
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads) quantize_flat_kernel(const float* __restrict__ x,
                                                                  uint8_t* __restrict__ q, int64_t n,
-                                                                 float scale, float zpf, int vec_ok) {
+                                                                 float scale, float zpf, int vec_ok,
+                                                                 const float* const* __restrict__ xslot) {
+  if (xslot) x = *xslot;   // source address read at run time (CUDA-graph replay on a new input buffer)
+  const int64_t nvec = vec_ok ? (n >> 2) : 0;   // float4 groups -> one output word each
+  const float rcp = __frcp_rn(scale);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  uint32_t* q32 = reinterpret_cast<uint32_t*>(q);
+  for (int64_t base = (int64_t)blockIdx.x * (kThreads * kU); base < nvec; base += (int64_t)gridDim.x * (kThreads * kU)) {
+    float4 f[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int64_t v = base + j * kThreads + threadIdx.x;
+      f[j] = (v < nvec) ? ld_stream_f4(x4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int64_t v = base + j * kThreads + threadIdx.x;
+      uint32_t w;
+      if (FAST) {
+        w = quant_u8_wrap_fast(f[j].x, scale, rcp, zpf) | (quant_u8_wrap_fast(f[j].y, scale, rcp, zpf) << 8) |
+            (quant_u8_wrap_fast(f[j].z, scale, rcp, zpf) << 16) | (quant_u8_wrap_fast(f[j].w, scale, rcp, zpf) << 24);
+      } else {
+        w = quant_u8_wrap(f[j].x, scale, zpf) | (quant_u8_wrap(f[j].y, scale, zpf) << 8) |
+            (quant_u8_wrap(f[j].z, scale, zpf) << 16) | (quant_u8_wrap(f[j].w, scale, zpf) << 24);
+      }
+      if (v < nvec) st_stream_u32(q32 + v, w);
+    }
+  }
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  int64_t nvec = vec_ok ? (n >> 4) : 0;
-  for (int64_t v = tid; v < nvec; v += nthreads) {
-    const float4* p = reinterpret_cast<const float4*>(x) + v * 4;
-    float4 f0 = ld_stream_f4(p), f1 = ld_stream_f4(p + 1), f2 = ld_stream_f4(p + 2), f3 = ld_stream_f4(p + 3);
-    uint4 o;
-    o.x = quant_u8_wrap(f0.x, scale, zpf) | (quant_u8_wrap(f0.y, scale, zpf) << 8) |
-          (quant_u8_wrap(f0.z, scale, zpf) << 16) | (quant_u8_wrap(f0.w, scale, zpf) << 24);
-    o.y = quant_u8_wrap(f1.x, scale, zpf) | (quant_u8_wrap(f1.y, scale, zpf) << 8) |
-          (quant_u8_wrap(f1.z, scale, zpf) << 16) | (quant_u8_wrap(f1.w, scale, zpf) << 24);
-    o.z = quant_u8_wrap(f2.x, scale, zpf) | (quant_u8_wrap(f2.y, scale, zpf) << 8) |
-          (quant_u8_wrap(f2.z, scale, zpf) << 16) | (quant_u8_wrap(f2.w, scale, zpf) << 24);
-    o.w = quant_u8_wrap(f3.x, scale, zpf) | (quant_u8_wrap(f3.y, scale, zpf) << 8) |
-          (quant_u8_wrap(f3.z, scale, zpf) << 16) | (quant_u8_wrap(f3.w, scale, zpf) << 24);
-    st_stream_u4(reinterpret_cast<uint4*>(q) + v, o);
-  }
-  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) q[i] = (uint8_t)quant_u8_wrap(x[i], scale, zpf);
+  for (int64_t i = (nvec << 2) + tid; i < n; i += nthreads) q[i] = (uint8_t)quant_u8_wrap(x[i], scale, zpf);
 }
 
 // ---- A1 fused with NCHW(f32) -> NHWC(u8, pitch cp) ---------------------------
@@ -64,7 +83,8 @@ __global__ void __launch_bounds__(kThreads) quantize_flat_kernel(const float* __
 // the same plane (coalesced) and write one 16-byte NHWC segment each.
 __global__ void __launch_bounds__(kThreads) quantize_nchw_nhwc_kernel(
     const float* __restrict__ x, uint8_t* __restrict__ q, int n, int c, int hw, int cp, float scale,
-    float zpf, uint32_t zpb) {
+    float zpf, uint32_t zpb, const float* const* __restrict__ xslot) {
+  if (xslot) x = *xslot;
   const int groups = cp >> 4;
   const int64_t total = (int64_t)n * hw * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -91,27 +111,39 @@ __global__ void __launch_bounds__(kThreads) quantize_nchw_nhwc_kernel(
 }
 
 // ---- A5 dequantize u8 -> f32 (flat) -----------------------------------------
+// One 32-bit load (4 codes) and one 128-bit store per thread and step, both warp-contiguous;
+// kUD steps in flight. (float)(q - zp) is built without a convert: 0x4B0000qq is the float
+// 2^23 + q, and (2^23 + q) - (2^23 + zp) is exact.
+constexpr int kUD = 8;
+
 __global__ void __launch_bounds__(kThreads) dequantize_flat_kernel(const uint8_t* __restrict__ q,
                                                                    float* __restrict__ x, int64_t n,
                                                                    float scale, int zp, int vec_ok) {
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  int64_t nvec = vec_ok ? (n >> 4) : 0;
-  for (int64_t v = tid; v < nvec; v += nthreads) {
-    const uint4 in = ld_stream_u4(reinterpret_cast<const uint4*>(q) + v);
-    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
-    float4* o = reinterpret_cast<float4*>(x) + v * 4;
+  const int64_t nvec = vec_ok ? (n >> 2) : 0;
+  const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+  float4* x4 = reinterpret_cast<float4*>(x);
+  const float bias = 8388608.f + (float)zp;
+  for (int64_t base = (int64_t)blockIdx.x * (kThreads * kUD); base < nvec; base += (int64_t)gridDim.x * (kThreads * kUD)) {
+    uint32_t w[kUD];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kUD; ++j) {
+      const int64_t v = base + j * kThreads + threadIdx.x;
+      w[j] = (v < nvec) ? ld_stream_u32(q32 + v) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kUD; ++j) {
+      const int64_t v = base + j * kThreads + threadIdx.x;
       float4 f;
-      f.x = dequant_f32(w[j] & 0xff, zp, scale);
-      f.y = dequant_f32((w[j] >> 8) & 0xff, zp, scale);
-      f.z = dequant_f32((w[j] >> 16) & 0xff, zp, scale);
-      f.w = dequant_f32(w[j] >> 24, zp, scale);
-      st_stream_f4(o + j, f);
+      f.x = __fmul_rn(__fsub_rn(__uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7650)), bias), scale);
+      f.y = __fmul_rn(__fsub_rn(__uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7651)), bias), scale);
+      f.z = __fmul_rn(__fsub_rn(__uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7652)), bias), scale);
+      f.w = __fmul_rn(__fsub_rn(__uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7653)), bias), scale);
+      if (v < nvec) st_stream_f4(x4 + v, f);
     }
   }
-  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) x[i] = dequant_f32(q[i], zp, scale);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (nvec << 2) + tid; i < n; i += nthreads) x[i] = dequant_f32(q[i], zp, scale);
 }
 
 __global__ void dequantize_rows_kernel(const uint8_t* __restrict__ q, float* __restrict__ x, int rows,
@@ -125,24 +157,41 @@ __global__ void dequantize_rows_kernel(const uint8_t* __restrict__ q, float* __r
 }
 
 // ---- A4 down_scale s32 -> u8 (flat) -------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads) downscale_flat_kernel(const int32_t* __restrict__ acc,
                                                                   uint8_t* __restrict__ y, int64_t n,
                                                                   float sa, float sb, float sc,
                                                                   float zpf, int vec_ok) {
+  const int64_t nvec = vec_ok ? (n >> 2) : 0;
+  const RequantFast2 rq = make_requant_fast2(sa, sb, sc, __frcp_rn(sc), zpf);
+  const uint4* a4 = reinterpret_cast<const uint4*>(acc);
+  uint32_t* y32 = reinterpret_cast<uint32_t*>(y);
+  for (int64_t base = (int64_t)blockIdx.x * (kThreads * kU); base < nvec; base += (int64_t)gridDim.x * (kThreads * kU)) {
+    uint4 a[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int64_t v = base + j * kThreads + threadIdx.x;
+      a[j] = (v < nvec) ? ld_stream_u4(a4 + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int64_t v = base + j * kThreads + threadIdx.x;
+      uint32_t w;
+      if (FAST) {
+        uint32_t y0, y1, y2, y3;
+        requant2_u8_fast<false>((int)a[j].x, (int)a[j].y, rq, y0, y1);
+        requant2_u8_fast<false>((int)a[j].z, (int)a[j].w, rq, y2, y3);
+        w = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+      } else {
+        w = requant_u8((int)a[j].x, sa, sb, sc, zpf) | (requant_u8((int)a[j].y, sa, sb, sc, zpf) << 8) |
+            (requant_u8((int)a[j].z, sa, sb, sc, zpf) << 16) | (requant_u8((int)a[j].w, sa, sb, sc, zpf) << 24);
+      }
+      if (v < nvec) st_stream_u32(y32 + v, w);
+    }
+  }
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  int64_t nvec = vec_ok ? (n >> 4) : 0;
-  for (int64_t v = tid; v < nvec; v += nthreads) {
-    const uint4* p = reinterpret_cast<const uint4*>(acc) + v * 4;
-    uint4 a[4] = {ld_stream_u4(p), ld_stream_u4(p + 1), ld_stream_u4(p + 2), ld_stream_u4(p + 3)};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o[j] = requant_u8((int)a[j].x, sa, sb, sc, zpf) | (requant_u8((int)a[j].y, sa, sb, sc, zpf) << 8) |
-             (requant_u8((int)a[j].z, sa, sb, sc, zpf) << 16) | (requant_u8((int)a[j].w, sa, sb, sc, zpf) << 24);
-    st_stream_u4(reinterpret_cast<uint4*>(y) + v, make_uint4(o[0], o[1], o[2], o[3]));
-  }
-  for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) y[i] = (uint8_t)requant_u8(acc[i], sa, sb, sc, zpf);
+  for (int64_t i = (nvec << 2) + tid; i < n; i += nthreads) y[i] = (uint8_t)requant_u8(acc[i], sa, sb, sc, zpf);
 }
 
 // ---- A9 min/max reduction ------------------------------------------------------
@@ -240,6 +289,14 @@ __global__ void __launch_bounds__(kThreads) relu_flat_kernel(const uint8_t* __re
   }
   const uint8_t z = (uint8_t)(zp4 & 0xff);
   for (int64_t i = (nvec << 4) + tid; i < n; i += nthreads) y[i] = x[i] > z ? x[i] : z;
+}
+
+// ---- indirect copy: materialises a run-time-addressed source into a fixed buffer --------------
+__global__ void __launch_bounds__(kThreads) copy_indirect_kernel(const uint4* const* __restrict__ slot,
+                                                                 uint4* __restrict__ dst, int64_t nvec) {
+  const uint4* __restrict__ src = *slot;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x)
+    st_stream_u4(dst + v, ld_stream_u4(src + v));
 }
 
 // ---- A11 max_pool2d<u8>, NHWC --------------------------------------------------
@@ -430,30 +487,63 @@ int i8ie_device_check(void) {
   return I8IE_OK;
 }
 
-int i8ie_quantize_f32_u8(const float* x, uint8_t* q, int64_t n, float scale, int zp, void* stream) {
+static int quantize_flat(const float* x, const float* const* xslot, uint8_t* q, int64_t n, float scale, int zp,
+                         void* stream) {
   I8IE_REQUIRE(n >= 0 && zp >= 0 && zp <= 255, "quantize: bad n/zp");
   if (n == 0) return I8IE_OK;
-  const int vec = aligned16(x) && aligned16(q);
-  quantize_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      x, q, n, scale, (float)zp, vec);
+  const int vec = (xslot || aligned16(x)) && aligned4(q);
+  const int grid = stream_grid((n + 3) / 4, kThreads * kU);
+  if (quant_fast_ok(scale))
+    quantize_flat_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot);
+  else
+    quantize_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot);
   return check_launch("quantize_flat_kernel");
 }
 
-int i8ie_quantize_nchw_f32_nhwc_u8(const float* x, uint8_t* q, int n, int c, int h, int w, int cp,
-                                   float scale, int zp, void* stream) {
+int i8ie_quantize_f32_u8(const float* x, uint8_t* q, int64_t n, float scale, int zp, void* stream) {
+  return quantize_flat(x, nullptr, q, n, scale, zp, stream);
+}
+
+int i8ie_quantize_f32_u8_indirect(const float* const* x_slot, uint8_t* q, int64_t n, float scale, int zp,
+                                  void* stream) {
+  I8IE_REQUIRE(x_slot != nullptr, "quantize_indirect: null slot");
+  return quantize_flat(nullptr, x_slot, q, n, scale, zp, stream);
+}
+
+int i8ie_copy_indirect(const void* const* src_slot, void* dst, int64_t nbytes, void* stream) {
+  I8IE_REQUIRE(src_slot && dst && nbytes >= 0 && nbytes % 16 == 0 && aligned16(dst), "copy_indirect: bad arguments");
+  if (nbytes == 0) return I8IE_OK;
+  copy_indirect_kernel<<<stream_grid(nbytes / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4* const*>(src_slot), reinterpret_cast<uint4*>(dst), nbytes / 16);
+  return check_launch("copy_indirect_kernel");
+}
+
+static int quantize_nhwc(const float* x, const float* const* xslot, uint8_t* q, int n, int c, int h, int w, int cp,
+                         float scale, int zp, void* stream) {
   I8IE_REQUIRE(cp % 16 == 0 && cp >= c && zp >= 0 && zp <= 255 && aligned16(q), "quantize_nhwc: bad cp/zp/alignment");
   const int64_t items = (int64_t)n * h * w * (cp / 16);
   if (items == 0) return I8IE_OK;
   quantize_nchw_nhwc_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      x, q, n, c, h * w, cp, scale, (float)zp, (uint32_t)zp);
+      x, q, n, c, h * w, cp, scale, (float)zp, (uint32_t)zp, xslot);
   return check_launch("quantize_nchw_nhwc_kernel");
+}
+
+int i8ie_quantize_nchw_f32_nhwc_u8(const float* x, uint8_t* q, int n, int c, int h, int w, int cp,
+                                   float scale, int zp, void* stream) {
+  return quantize_nhwc(x, nullptr, q, n, c, h, w, cp, scale, zp, stream);
+}
+
+int i8ie_quantize_nchw_f32_nhwc_u8_indirect(const float* const* x_slot, uint8_t* q, int n, int c, int h, int w,
+                                            int cp, float scale, int zp, void* stream) {
+  I8IE_REQUIRE(x_slot != nullptr, "quantize_nhwc_indirect: null slot");
+  return quantize_nhwc(nullptr, x_slot, q, n, c, h, w, cp, scale, zp, stream);
 }
 
 int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, int zp, void* stream) {
   I8IE_REQUIRE(n >= 0, "dequantize: bad n");
   if (n == 0) return I8IE_OK;
-  const int vec = aligned16(x) && aligned16(q);
-  dequantize_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+  const int vec = aligned16(x) && aligned4(q) && zp >= 0 && zp <= 255;
+  dequantize_flat_kernel<<<stream_grid((n + 3) / 4, kThreads * kUD), kThreads, 0, (cudaStream_t)stream>>>(
       q, x, n, scale, zp, vec);
   return check_launch("dequantize_flat_kernel");
 }
@@ -471,9 +561,12 @@ int i8ie_downscale_s32_u8(const int32_t* acc, uint8_t* y, int64_t n, float sa, f
                           int zp_c, void* stream) {
   I8IE_REQUIRE(n >= 0, "downscale: bad n");
   if (n == 0) return I8IE_OK;
-  const int vec = aligned16(acc) && aligned16(y);
-  downscale_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      acc, y, n, sa, sb, sc, (float)zp_c, vec);
+  const int vec = aligned16(acc) && aligned4(y);
+  const int grid = stream_grid((n + 3) / 4, kThreads * kU);
+  if (requant_fast_ok(sa, sb, sc))
+    downscale_flat_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
+  else
+    downscale_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
   return check_launch("downscale_flat_kernel");
 }
 

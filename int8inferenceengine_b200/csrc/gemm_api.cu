@@ -120,6 +120,9 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
     p->stem2 = tc_stem2_eligible(g, c) && std::getenv("I8IE_NO_STEM2") == nullptr;
     p->bk = 64;
     p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
+    // stem2 covers all real channels with one N tile and fills the pad lanes with plain stores
+    if (p->stem2 && tc_pick_bn(kc) < p->bn && tc_pick_bn(kc) % 32 == 0 && tc_pick_bn(kc) >= kc && kc_pad >= tc_pick_bn(kc))
+      p->bn = tc_pick_bn(kc);
     if (cudaMalloc(&p->stem_x, (size_t)p->stem.bytes) != cudaSuccess ||
         cudaMalloc(&p->stem_w, (size_t)kc_pad * kh * 64) != cudaSuccess) {
       set_error("conv2d_plan_create: cudaMalloc of the stem buffers failed");
@@ -193,18 +196,33 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   return launch_simt_igemm(plan->g, x, plan->w_packed, y, ep, zp_in, (cudaStream_t)stream);
 }
 
-int i8ie_conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, float in_scale, int in_zp, uint8_t* y,
-                       const int32_t* oc, float sb, float sc, int zp_out, int flags, int32_t* acc_out,
-                       void* stream) {
-  I8IE_REQUIRE(plan && x_nchw && y && oc, "conv2d_f32_u8: null argument");
+static int conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, const float* const* x_slot, float in_scale,
+                        int in_zp, uint8_t* y, const int32_t* oc, float sb, float sc, int zp_out, int flags,
+                        int32_t* acc_out, void* stream) {
+  I8IE_REQUIRE(plan && (x_nchw || x_slot) && y && oc, "conv2d_f32_u8: null argument");
   I8IE_REQUIRE(plan->impl == 3, "conv2d_f32_u8: only stem plans fuse the input quantise (plan impl=%d)", plan->impl);
   I8IE_REQUIRE(in_zp >= 0 && in_zp <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_f32_u8: zero point out of range");
   EpiParams ep{oc, nullptr, in_scale, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
-  int rc = tc_stem_quantize_input(plan->g, plan->stem, x_nchw, plan->stem_x, in_scale, in_zp, (cudaStream_t)stream);
+  int rc = tc_stem_quantize_input(plan->g, plan->stem, x_nchw, x_slot, plan->stem_x, in_scale, in_zp,
+                                  (cudaStream_t)stream);
   if (rc != I8IE_OK) return rc;
   if (plan->stem2)
     return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
   return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+}
+
+int i8ie_conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, float in_scale, int in_zp, uint8_t* y,
+                       const int32_t* oc, float sb, float sc, int zp_out, int flags, int32_t* acc_out,
+                       void* stream) {
+  I8IE_REQUIRE(x_nchw != nullptr, "conv2d_f32_u8: null input");
+  return conv2d_f32_u8(plan, x_nchw, nullptr, in_scale, in_zp, y, oc, sb, sc, zp_out, flags, acc_out, stream);
+}
+
+int i8ie_conv2d_f32_u8_indirect(i8ie_conv_plan* plan, const float* const* x_slot, float in_scale, int in_zp,
+                                uint8_t* y, const int32_t* oc, float sb, float sc, int zp_out, int flags,
+                                int32_t* acc_out, void* stream) {
+  I8IE_REQUIRE(x_slot != nullptr, "conv2d_f32_u8_indirect: null slot");
+  return conv2d_f32_u8(plan, nullptr, x_slot, in_scale, in_zp, y, oc, sb, sc, zp_out, flags, acc_out, stream);
 }
 
 int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,

@@ -49,7 +49,8 @@ bool tc_stem_eligible(const GemmGeom& g, int c);
 StemGeom tc_stem_geom(const GemmGeom& g, int c);
 int tc_stem_pack_weights(const GemmGeom& g, int c, const int8_t* w_packed, int8_t* ws, cudaStream_t stream);
 int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, uint8_t* xs, int zp, cudaStream_t stream);
-int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, uint8_t* xs, float scale, int zp,
+int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, const float* const* xslot,
+                           uint8_t* xs, float scale, int zp,
                            cudaStream_t stream);
 int tc_encode_stem_act_map(CUtensorMap* tm, const uint8_t* xs, const GemmGeom& g, const StemGeom& s);
 bool tc_stem2_eligible(const GemmGeom& g, int c);

@@ -101,8 +101,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
   const float zpf = (float)p.ep.zp_out;
   const float sa = p.ep.sa, sb = p.ep.sb, sc = p.ep.sc;
   const bool has_bias = p.ep.bias_f != nullptr;
-  // relu<u8> is max(y, zero_point): folded into the lower clamp bound (functional.cc:22-23)
-  const float lo = p.ep.relu ? zpf : 0.f;
+  const RequantFast2 rq = make_requant_fast2(sa, sb, sc, rcp, zpf);
   uint8_t* yrow = p.y + (size_t)(m < 0 ? 0 : m) * p.out_cp;
 #pragma unroll 1
   for (int c0 = half * 32; c0 < BN; c0 += 64) {
@@ -140,16 +139,14 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
         if (n0 + c0 + j < p.N) p.ep.acc_out[(size_t)m * p.N + n0 + c0 + j] = (int32_t)v[j];
     }
     if (p.fast_requant) {
-      // exact requantise (see requant_u8_fast); the truncating convert is a round-down add of
-      // 2^23, which leaves floor(r) in the low mantissa byte (r is already clamped to [0,255])
+      // exact requantise, two accumulators per packed fp32x2 instruction (see requant2_u8_fast);
+      // clamp + truncation are one saturating convert, relu is a max before it
+      if (p.ep.relu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float d = __fmul_rn(__fmul_rn(__int2float_rn((int32_t)v[j]), sa), sb);
-        const float q0 = __fmul_rn(d, rcp);
-        const float e = __fmaf_rn(-sc, q0, d);
-        const float q = __fmaf_rn(e, rcp, q0);
-        const float r = fminf(fmaxf(__fadd_rn(q, zpf), lo), 255.f);
-        v[j] = __float_as_uint(__fadd_rd(r, 8388608.f));
+        for (int j = 0; j < 32; j += 2) requant2_u8_fast<true>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) requant2_u8_fast<false>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
       }
     } else {
       const uint32_t zlo = p.ep.relu ? (uint32_t)p.ep.zp_out : 0u;
@@ -391,6 +388,7 @@ struct Stem2Params {
   int pairs;        // ceil(oh / 2) output-row pairs per image
   int nsl;          // 1 KB slots per region = ceil((kh + 4) / 4)
   int stages;
+  int dbg;          // dev-only bottleneck probes (I8IE_STEM2_DBG): 1 = no epilogue, 2 = no MMA, 4 = no loads, 8 = no stores
   const uint8_t* xs;
 };
 
@@ -444,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
         const int i0 = 4 * p0;
         int nrows = sp.hp - i0;
         if (nrows > rows_per_tile) nrows = rows_per_tile;
+        if (sp.dbg & 4) { ptx::mbar_arrive(&ctl->full[s]); continue; }
         ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)nrows * row_bytes);
         uint8_t* st = sA + (size_t)s * a_stage;
         const uint8_t* src = sp.xs + ((size_t)img * sp.hp + i0) * row_bytes;
@@ -506,8 +505,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
       if (!ok) atomicCAS(&g_tc_error, 0, 3);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
-      epilogue_row<BN>(p, t_row, ok ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]), ptx::smem_u32(ctl->bias[0]), nullptr, rcp,
-                       (warp - 2) >> 2);
+      if (!(sp.dbg & 1)) {
+        epilogue_row<BN>(p, t_row, (ok && !(sp.dbg & 8)) ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]),
+                         ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2);
+        // output pitch wider than the N tile (e.g. 96 channels stored at pitch 128): the pad lanes
+        // carry the zero point; written by the warp of each pair that had fewer chunks
+        if (BN < p.out_cp && ((warp - 2) >> 2) == ((BN / 32) & 1) && ok && m >= 0) {
+          const uint32_t z4 = (uint32_t)p.ep.zp_out * 0x01010101u;
+          for (int c = BN; c < p.out_cp; c += 16)
+            *reinterpret_cast<uint4*>(p.y + (size_t)m * p.out_cp + c) = make_uint4(z4, z4, z4, z4);
+        }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
@@ -580,29 +588,69 @@ __global__ void stem_pack_kernel(const uint8_t* __restrict__ x, uint8_t* __restr
 }
 
 // Same layout, produced straight from the fp32 NCHW image with the input quantise
-// (quantize_utils.cc:44-52) fused in.
-__global__ void stem_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs, int n, int c, int h,
-                                     int w, int pad, int hp, int wsp, float scale, float zpf, uint32_t zp) {
+// (quantize_utils.cc:44-52) fused in. One thread per superpixel (4 px x 4 lanes = one 128-bit
+// store). VEC2: pad and w even -> the 4 pixels are two aligned float2 per channel plane.
+// FAST: division by the hoisted reciprocal with FMA correction (quant_u8_wrap_fast).
+template <bool VEC2, bool FAST>
+__global__ void __launch_bounds__(256) stem_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs,
+                                                            int n, int c, int h, int w, int pad, int hp, int wsp,
+                                                            float scale, float zpf, uint32_t zp,
+                                                            const float* const* __restrict__ xslot) {
+  if (xslot) x = *xslot;   // run-time source address (CUDA-graph replay on a new input buffer)
   const int64_t total = (int64_t)n * hp * wsp;
+  const float rcp = __frcp_rn(scale);
+  const int64_t plane = (int64_t)h * w;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int sx = (int)(t % wsp);
     const int y = (int)((t / wsp) % hp);
     const int img = (int)(t / ((int64_t)wsp * hp));
     const int row = y - pad;
-    uint32_t wd[4];
+    const uint32_t zp4 = zp * 0x01010101u;
+    uint32_t wd[4] = {zp4, zp4, zp4, zp4};
+    if (row >= 0 && row < h) {
+      const int col0 = sx * 4 - pad;
+      const float* src = x + ((int64_t)img * c * h + row) * w + col0;
+      float f[4][4];   // [channel lane][pixel]
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = sx * 4 + j - pad;
-      uint32_t v = zp * 0x01010101u;
-      if (row >= 0 && row < h && col >= 0 && col < w) {
-        const float* src = x + ((int64_t)img * c * h + row) * w + col;
-        v = 0;
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[ch][j] = 0.f;
+      if (VEC2) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < c) {
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+              if (col0 + j >= 0 && col0 + j < w) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(src + ch * plane + j));
+                f[ch][j] = v.x; f[ch][j + 1] = v.y;
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
-          v |= ((ch < c) ? quant_u8_wrap(__ldg(src + (int64_t)ch * h * w), scale, zpf) : zp) << (8 * ch);
+          if (ch < c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col0 + j >= 0 && col0 + j < w) f[ch][j] = __ldg(src + ch * plane + j);
       }
-      wd[j] = v;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (col0 + j >= 0 && col0 + j < w) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t q = (ch < c) ? (FAST ? quant_u8_wrap_fast(f[ch][j], scale, rcp, zpf)
+                                                : quant_u8_wrap(f[ch][j], scale, zpf))
+                                        : zp;
+            v |= q << (8 * ch);
+          }
+          wd[j] = v;
+        }
+      }
     }
     *reinterpret_cast<uint4*>(xs + t * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
   }
@@ -980,13 +1028,20 @@ int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, u
   return check_launch("stem_pack_kernel");
 }
 
-int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, uint8_t* xs, float scale, int zp,
-                           cudaStream_t stream) {
+int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, const float* const* xslot,
+                           uint8_t* xs, float scale, int zp, cudaStream_t stream) {
   const int64_t total = (int64_t)g.n * s.hp * s.wsp;
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  stem_quantize_kernel<<<blocks, 256, 0, stream>>>(x, xs, g.n, s.c, g.h, g.w, g.pad, s.hp, s.wsp, scale, (float)zp,
-                                                 (uint32_t)zp);
+  const bool vec2 = (g.pad % 2 == 0) && (g.w % 2 == 0) && (xslot || (reinterpret_cast<uintptr_t>(x) & 7) == 0);
+  const bool fast = quant_fast_ok(scale);
+#define I8IE_STEMQ(V, F) stem_quantize_kernel<V, F><<<blocks, 256, 0, stream>>>( \
+      x, xs, g.n, s.c, g.h, g.w, g.pad, s.hp, s.wsp, scale, (float)zp, (uint32_t)zp, xslot)
+  if (vec2 && fast) I8IE_STEMQ(true, true);
+  else if (vec2) I8IE_STEMQ(true, false);
+  else if (fast) I8IE_STEMQ(false, true);
+  else I8IE_STEMQ(false, false);
+#undef I8IE_STEMQ
   return check_launch("stem_quantize_kernel");
 }
 
@@ -1034,6 +1089,8 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   sp.pairs = (g.oh + 1) / 2;
   sp.nsl = (g.kh + 4 + 3) / 4;
   sp.xs = xs;
+  sp.dbg = 0;
+  if (const char* e = std::getenv("I8IE_STEM2_DBG")) sp.dbg = std::atoi(e);
   const int w_bytes = g.kh * BN * 64;
   const int a_stage = 4 * sp.nsl * 1024;
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
@@ -1060,6 +1117,7 @@ int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  I8IE_REQUIRE(bn % 32 == 0 || bn >= g.out_cp, "stem2: N tile %d narrower than the output pitch must be a multiple of 32", bn);
   switch (bn) {
     case 32:  return launch_stem2_bn<32>(g, s, xs, tmB, p, stream);
     case 64:  return launch_stem2_bn<64>(g, s, xs, tmB, p, stream);

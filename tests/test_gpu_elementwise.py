@@ -27,6 +27,51 @@ def test_quantize_flat(n, scale, zp):
     assert np.array_equal(q.cpu().numpy(), port.quantize(x, np.float32(scale), zp))
 
 
+def test_quantize_extreme_values_match_x86_cast():
+    """inf / NaN / beyond-int32 / denormal inputs: the reference's cast is cvttss2si + low byte."""
+    specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 3e38, -3e38, 1e30, -1e30, 1e18, -1e18, 9.9e17,
+                         2.0**31 * 0.025, 2.0**31 * 0.025 * 1.0001, -2.0**31 * 0.025, 5.3e7, -5.3e7, 5.4e7,
+                         1e-45, -1e-45, 1e-38, -1e-38, 1e-30, 6.374, 6.375, 6.376, -3.175, -3.2, 3.2],
+                        dtype=np.float32)
+    rng = np.random.default_rng(7)
+    big = (rng.standard_normal(4096) * 10.0 ** rng.uniform(-40, 38, size=4096)).astype(np.float32)
+    x = np.concatenate([specials, big])
+    q = torch.empty(x.size, dtype=torch.uint8, device="cuda")
+    for scale, zp in [(0.025, 127), (1.0, 0), (3.7e-5, 255), (812.5, 3), (1e-19, 10), (2e18, 10)]:
+        _check(lib().i8ie_quantize_f32_u8(dev(x).data_ptr(), q.data_ptr(), x.size, scale, zp, stream()))
+        assert np.array_equal(q.cpu().numpy(), port.quantize(x, np.float32(scale), zp)), (scale, zp)
+
+
+def test_quantize_rounding_boundaries():
+    """x just below / at / above k*scale for every code k: the truncation boundaries of x/scale + zp,
+    where a quotient that is off by one ulp would change the result."""
+    k = np.arange(-300, 600, dtype=np.float64)
+    for scale, zp in [(0.025, 127), (0.0371, 100), (0.1, 0), (1.0 / 3.0, 17), (0.0078125, 128), (1.7, 250)]:
+        s32 = np.float32(scale)
+        centre = (k * float(s32)).astype(np.float32)
+        xs = [centre]
+        for _ in range(3):
+            xs.append(np.nextafter(xs[-1], np.float32(np.inf)))
+        lo = centre
+        for _ in range(3):
+            lo = np.nextafter(lo, np.float32(-np.inf))
+            xs.append(lo)
+        x = np.concatenate(xs).astype(np.float32)
+        q = torch.empty(x.size, dtype=torch.uint8, device="cuda")
+        _check(lib().i8ie_quantize_f32_u8(dev(x).data_ptr(), q.data_ptr(), x.size, float(s32), zp, stream()))
+        assert np.array_equal(q.cpu().numpy(), port.quantize(x, s32, zp)), (scale, zp)
+
+
+def test_quantize_dense_float_sweep():
+    """Every float32 in a band of consecutive bit patterns (2^22 of them) for the default input qparams."""
+    bits = np.arange(0x3F000000, 0x3F000000 + (1 << 22), dtype=np.uint32)   # [0.5, 1.0)
+    for sign in (0, 0x80000000):
+        x = (bits | np.uint32(sign)).view(np.float32)
+        q = torch.empty(x.size, dtype=torch.uint8, device="cuda")
+        _check(lib().i8ie_quantize_f32_u8(dev(x).data_ptr(), q.data_ptr(), x.size, 0.025, 127, stream()))
+        assert np.array_equal(q.cpu().numpy(), port.quantize(x, np.float32(0.025), 127))
+
+
 def test_quantize_misaligned_and_golden():
     g = load_golden("kat_elementwise")
     for tag in ["a", "b", "edge", "c"]:
@@ -60,6 +105,24 @@ def test_dequantize_flat(n):
     x = torch.empty(n, dtype=torch.float32, device="cuda")
     _check(lib().i8ie_dequantize_u8_f32(dev(q).data_ptr(), x.data_ptr(), n, 0.0417, 93, stream()))
     assert np.array_equal(x.cpu().numpy(), port.dequantize(q, np.float32(0.0417), 93))
+
+
+def test_dequantize_all_codes_all_zero_points():
+    q = np.tile(np.arange(256, dtype=np.uint8), 5)[: 256 * 5 - 3]
+    x = torch.empty(q.size, dtype=torch.float32, device="cuda")
+    for zp in [0, 1, 93, 127, 128, 254, 255]:
+        for scale in [0.0417, 1.0, 3.3e-7, 1234.5]:
+            _check(lib().i8ie_dequantize_u8_f32(dev(q).data_ptr(), x.data_ptr(), q.size, scale, zp, stream()))
+            assert np.array_equal(x.cpu().numpy(), port.dequantize(q, np.float32(scale), zp)), (zp, scale)
+
+
+def test_dequantize_misaligned():
+    rng = np.random.default_rng(11)
+    q = rng.integers(0, 256, size=1000 + 1, dtype=np.uint8)
+    qd = dev(q)
+    x = torch.empty(1000 + 1, dtype=torch.float32, device="cuda")
+    _check(lib().i8ie_dequantize_u8_f32(qd.data_ptr() + 1, x.data_ptr() + 4, 1000, 0.2, 127, stream()))
+    assert np.array_equal(x.cpu().numpy()[1:], port.dequantize(q[1:], np.float32(0.2), 127))
 
 
 def test_dequantize_rows():
