@@ -187,6 +187,38 @@ __device__ __forceinline__ int32_t dp4a_u8s8(uint32_t a, uint32_t b, int32_t c) 
   return d;
 }
 
+// Four elements at once, NO guards: valid when every |x| < quant_fast_limit(scale) (then all
+// intermediates are normal and |x/scale + zp| < 2^31, so the x86 cast is a plain truncation);
+// NaN falls through to byte 0 like the reference. Two packed fp32x2 chains + four converts.
+struct QuantFast2 {
+  f32x2_t rcp, nscale, zp;
+};
+__device__ __forceinline__ QuantFast2 make_quant_fast2(float scale, float rcp, float zpf) {
+  QuantFast2 c;
+  c.rcp = f2_pack(rcp, rcp); c.nscale = f2_pack(-scale, -scale); c.zp = f2_pack(zpf, zpf);
+  return c;
+}
+__device__ __forceinline__ void quant2_fast(float x0, float x1, const QuantFast2& c, int& i0, int& i1) {
+  const f32x2_t x = f2_pack(x0, x1);
+  const f32x2_t q0 = f2_mul(x, c.rcp);
+  const f32x2_t e = f2_fma(c.nscale, q0, x);
+  const f32x2_t q = f2_fma(e, c.rcp, q0);
+  float v0, v1;
+  f2_unpack(f2_add(q, c.zp), v0, v1);
+  i0 = __float2int_rz(v0);
+  i1 = __float2int_rz(v1);
+}
+// low bytes of four ints -> one word
+__device__ __forceinline__ uint32_t pack_low_bytes(int i0, int i1, int i2, int i3) {
+  return __byte_perm(__byte_perm((uint32_t)i0, (uint32_t)i1, 0x0040), __byte_perm((uint32_t)i2, (uint32_t)i3, 0x0040), 0x5410);
+}
+__device__ __forceinline__ uint32_t quant4_fast(float a, float b, float c, float d, const QuantFast2& k) {
+  int i0, i1, i2, i3;
+  quant2_fast(a, b, k, i0, i1);
+  quant2_fast(c, d, k, i2, i3);
+  return pack_low_bytes(i0, i1, i2, i3);
+}
+
 // streaming (read-once) 128-bit loads / stores
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 r;
@@ -240,6 +272,13 @@ inline bool quant_fast_ok(float scale) {
   uint32_t bits;
   memcpy(&bits, &scale, sizeof(bits));
   return (bits & 0x7fffffu) != 0x7fffffu;
+}
+
+// Largest |x| for which the unguarded packed quantise (quant4_fast) is exact; 0 = never use it.
+inline float quant_fast_limit(float scale) {
+  if (!quant_fast_ok(scale)) return 0.f;
+  const float lim = 1073741824.f * scale;   // |x / scale| < 2^30, so |x/scale + zp| < 2^31
+  return lim < 1e18f ? lim : 1e18f;
 }
 
 // epilogue parameters shared by the SIMT and tcgen05 GEMM-shaped kernels

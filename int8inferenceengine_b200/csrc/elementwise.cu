@@ -46,10 +46,12 @@ template <bool FAST>
 __global__ void __launch_bounds__(kThreads) quantize_flat_kernel(const float* __restrict__ x,
                                                                  uint8_t* __restrict__ q, int64_t n,
                                                                  float scale, float zpf, int vec_ok,
-                                                                 const float* const* __restrict__ xslot) {
+                                                                 const float* const* __restrict__ xslot,
+                                                                 float fast_lim) {
   if (xslot) x = *xslot;   // source address read at run time (CUDA-graph replay on a new input buffer)
   const int64_t nvec = vec_ok ? (n >> 2) : 0;   // float4 groups -> one output word each
   const float rcp = __frcp_rn(scale);
+  const QuantFast2 qc = make_quant_fast2(scale, rcp, zpf);
   const float4* x4 = reinterpret_cast<const float4*>(x);
   uint32_t* q32 = reinterpret_cast<uint32_t*>(q);
   for (int64_t base = (int64_t)blockIdx.x * (kThreads * kU); base < nvec; base += (int64_t)gridDim.x * (kThreads * kU)) {
@@ -59,18 +61,30 @@ __global__ void __launch_bounds__(kThreads) quantize_flat_kernel(const float* __
       const int64_t v = base + j * kThreads + threadIdx.x;
       f[j] = (v < nvec) ? ld_stream_f4(x4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    uint32_t w[kU];
+    bool done = false;
+    if (FAST) {
+      // one magnitude test for the whole group, then the unguarded packed path
+      float amax = 0.f;
+#pragma unroll
+      for (int j = 0; j < kU; ++j)
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(f[j].x), fabsf(f[j].y))), fmaxf(fabsf(f[j].z), fabsf(f[j].w)));
+      if (amax < fast_lim) {
+#pragma unroll
+        for (int j = 0; j < kU; ++j) w[j] = quant4_fast(f[j].x, f[j].y, f[j].z, f[j].w, qc);
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int j = 0; j < kU; ++j)
+        w[j] = quant_u8_wrap(f[j].x, scale, zpf) | (quant_u8_wrap(f[j].y, scale, zpf) << 8) |
+               (quant_u8_wrap(f[j].z, scale, zpf) << 16) | (quant_u8_wrap(f[j].w, scale, zpf) << 24);
+    }
 #pragma unroll
     for (int j = 0; j < kU; ++j) {
       const int64_t v = base + j * kThreads + threadIdx.x;
-      uint32_t w;
-      if (FAST) {
-        w = quant_u8_wrap_fast(f[j].x, scale, rcp, zpf) | (quant_u8_wrap_fast(f[j].y, scale, rcp, zpf) << 8) |
-            (quant_u8_wrap_fast(f[j].z, scale, rcp, zpf) << 16) | (quant_u8_wrap_fast(f[j].w, scale, rcp, zpf) << 24);
-      } else {
-        w = quant_u8_wrap(f[j].x, scale, zpf) | (quant_u8_wrap(f[j].y, scale, zpf) << 8) |
-            (quant_u8_wrap(f[j].z, scale, zpf) << 16) | (quant_u8_wrap(f[j].w, scale, zpf) << 24);
-      }
-      if (v < nvec) st_stream_u32(q32 + v, w);
+      if (v < nvec) st_stream_u32(q32 + v, w[j]);
     }
   }
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,15 +314,103 @@ __global__ void __launch_bounds__(kThreads) copy_indirect_kernel(const uint4* co
 }
 
 // ---- A11 max_pool2d<u8>, NHWC --------------------------------------------------
-// One thread per (output pixel, 16-channel group): k*k 128-bit loads, byte-wise max.
-// KS > 0: window size known at compile time -> the k*k loads are all in flight before the
-// first max (the runtime-k loop serialises load -> max -> load and is latency-bound).
+// Byte-wise unsigned max of 16 channels, kept as even/odd bytes in u16x2 lanes: one tap word
+// costs 2 PRMT + 2 VIMNMX.U16x2 (the __vmaxu4 intrinsic is a 7-instruction emulation on sm_100).
+struct U8x16Max {
+  uint32_t e[4], o[4];
+  __device__ __forceinline__ void init() {   // min<u8_t>() == 0 (functional.cc:33-35)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { e[i] = 0; o[i] = 0; }
+  }
+  __device__ __forceinline__ void one(int i, uint32_t w) {
+    const uint32_t we = __byte_perm(w, 0, 0x4240), wo = __byte_perm(w, 0, 0x4341);
+    asm("max.u16x2 %0, %0, %1;" : "+r"(e[i]) : "r"(we));
+    asm("max.u16x2 %0, %0, %1;" : "+r"(o[i]) : "r"(wo));
+  }
+  __device__ __forceinline__ void tap(const uint4& v) { one(0, v.x); one(1, v.y); one(2, v.z); one(3, v.w); }
+  __device__ __forceinline__ uint4 result() const {
+    return make_uint4(__byte_perm(e[0], o[0], 0x6240), __byte_perm(e[1], o[1], 0x6240),
+                      __byte_perm(e[2], o[2], 0x6240), __byte_perm(e[3], o[3], 0x6240));
+  }
+};
+
+// window max of one (output pixel, 16-channel group); `base` points at the window's first tap.
+// Pad groups (all lanes hold the zero point everywhere) need a single tap.
+template <int KS>
+__device__ __forceinline__ uint4 pool_window(const uint8_t* __restrict__ base, int w, int cp, int ks_rt, bool pad_group) {
+  const int ks = KS > 0 ? KS : ks_rt;
+  if (pad_group) return __ldg(reinterpret_cast<const uint4*>(base));
+  U8x16Max m;
+  m.init();
+  if (KS > 0) {
+    uint4 v[KS > 0 ? KS * KS : 1];   // all k*k loads in flight before the first max
+#pragma unroll
+    for (int a = 0; a < KS; ++a)
+#pragma unroll
+      for (int b = 0; b < KS; ++b)
+        v[a * KS + b] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)a * w + b) * cp));
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) m.tap(v[i]);
+  } else {
+    for (int a = 0; a < ks; ++a)
+      for (int b = 0; b < ks; ++b) m.tap(__ldg(reinterpret_cast<const uint4*>(base + ((int64_t)a * w + b) * cp)));
+  }
+  return m.result();
+}
+
+// One block per output row (img, oy): thread = (ox, 16-channel group) — no per-thread division
+// chain when the group count is a power of two. NHWC output.
+template <int KS>
+__global__ void __launch_bounds__(kThreads) maxpool_nhwc_rows_kernel(const uint8_t* __restrict__ x,
+                                                                     uint8_t* __restrict__ y, int h, int w,
+                                                                     int c, int cp, int ks_rt, int st, int oh,
+                                                                     int ow, int gshift) {
+  const int groups = cp >> 4;
+  const int img = blockIdx.x / oh, oy = blockIdx.x - img * oh;
+  const uint8_t* xrow = x + ((int64_t)img * h + (int64_t)oy * st) * w * cp;
+  uint8_t* yrow = y + ((int64_t)img * oh + oy) * ow * cp;
+  for (int t = threadIdx.x; t < ow * groups; t += blockDim.x) {
+    const int ox = gshift >= 0 ? (t >> gshift) : (t / groups);
+    const int g = t - ox * groups;
+    const uint4 m = pool_window<KS>(xrow + (int64_t)ox * st * cp + g * 16, w, cp, ks_rt, g * 16 >= c);
+    *reinterpret_cast<uint4*>(yrow + (int64_t)ox * cp + g * 16) = m;
+  }
+}
+
+// Pool + flatten: one block per image; the NCHW-ordered result [c][oh*ow] is assembled in
+// shared memory and written out with coalesced 128-bit stores (it is contiguous per image).
+template <int KS>
+__global__ void __launch_bounds__(kThreads) maxpool_nhwc_to_nchw_image_kernel(const uint8_t* __restrict__ x,
+                                                                              uint8_t* __restrict__ y, int h,
+                                                                              int w, int c, int cp, int ks_rt,
+                                                                              int st, int oh, int ow) {
+  extern __shared__ __align__(16) uint8_t s_out[];
+  const int groups = (c + 15) >> 4;   // only groups holding real channels
+  const int img = blockIdx.x, plane = oh * ow;
+  const uint8_t* ximg = x + (int64_t)img * h * w * cp;
+  for (int t = threadIdx.x; t < plane * groups; t += blockDim.x) {
+    const int g = t % groups, pix = t / groups;
+    const int oy = pix / ow, ox = pix - oy * ow;
+    const uint4 m = pool_window<KS>(ximg + (((int64_t)oy * st) * w + (int64_t)ox * st) * cp + g * 16, w, cp, ks_rt, false);
+    const uint32_t wds[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ch = g * 16 + j;
+      if (ch < c) s_out[ch * plane + pix] = (uint8_t)(wds[j >> 2] >> (8 * (j & 3)));
+    }
+  }
+  __syncthreads();
+  const int total = c * plane;   // multiple of 16 (checked by the host)
+  uint4* dst = reinterpret_cast<uint4*>(y + (int64_t)img * total);
+  for (int v = threadIdx.x; v < (total >> 4); v += blockDim.x) dst[v] = reinterpret_cast<const uint4*>(s_out)[v];
+}
+
+// Generic fallback (any size, NCHW scatter): one thread per (output pixel, 16-channel group).
 template <int KS>
 __global__ void __launch_bounds__(kThreads) maxpool_nhwc_kernel(const uint8_t* __restrict__ x,
                                                                 uint8_t* __restrict__ y, int n, int h,
                                                                 int w, int c, int cp, int ks_rt, int st,
                                                                 int oh, int ow, int out_nchw) {
-  const int ks = KS > 0 ? KS : ks_rt;
   const int groups = cp >> 4;
   const int64_t total = (int64_t)n * oh * ow * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -319,25 +421,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_nhwc_kernel(const uint8_t* _
     const int oy = (int)(r % oh);
     const int img = (int)(r / oh);
     const uint8_t* base = x + (((int64_t)img * h + oy * st) * w + ox * st) * cp + g * 16;
-    uint4 m = make_uint4(0, 0, 0, 0);  // min<u8_t>() == 0 (functional.cc:33-35)
-    if (KS > 0) {
-      uint4 v[KS > 0 ? KS * KS : 1];
-#pragma unroll
-      for (int a = 0; a < KS; ++a)
-#pragma unroll
-        for (int b = 0; b < KS; ++b)
-          v[a * KS + b] = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)a * w + b) * cp));
-#pragma unroll
-      for (int i = 0; i < KS * KS; ++i) {
-        m.x = __vmaxu4(m.x, v[i].x); m.y = __vmaxu4(m.y, v[i].y); m.z = __vmaxu4(m.z, v[i].z); m.w = __vmaxu4(m.w, v[i].w);
-      }
-    } else {
-      for (int a = 0; a < ks; ++a)
-        for (int b = 0; b < ks; ++b) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + ((int64_t)a * w + b) * cp));
-          m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
-        }
-    }
+    const uint4 m = pool_window<KS>(base, w, cp, ks_rt, g * 16 >= c);
     if (!out_nchw) {
       *reinterpret_cast<uint4*>(y + (((int64_t)img * oh + oy) * ow + ox) * cp + g * 16) = m;
     } else {
@@ -493,10 +577,11 @@ static int quantize_flat(const float* x, const float* const* xslot, uint8_t* q, 
   if (n == 0) return I8IE_OK;
   const int vec = (xslot || aligned16(x)) && aligned4(q);
   const int grid = stream_grid((n + 3) / 4, kThreads * kU);
-  if (quant_fast_ok(scale))
-    quantize_flat_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot);
+  const float lim = quant_fast_limit(scale);
+  if (lim > 0.f)
+    quantize_flat_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot, lim);
   else
-    quantize_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot);
+    quantize_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot, 0.f);
   return check_launch("quantize_flat_kernel");
 }
 
@@ -609,13 +694,26 @@ int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int 
   const int oh = (h - ksize) / stride + 1, ow = (w - ksize) / stride + 1;
   const int64_t items = (int64_t)n * oh * ow * (cp / 16);
   if (items == 0) return I8IE_OK;
-  const int grid = stream_grid(items, kThreads);
-  if (ksize == 3)
-    maxpool_nhwc_kernel<3><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
-  else if (ksize == 2)
-    maxpool_nhwc_kernel<2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
-  else
-    maxpool_nhwc_kernel<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
+  cudaStream_t s = (cudaStream_t)stream;
+#define I8IE_POOL_KS(KERNEL, GRID, SMEM, ...)                                   \
+  do {                                                                          \
+    if (ksize == 3) KERNEL<3><<<GRID, kThreads, SMEM, s>>>(__VA_ARGS__);        \
+    else if (ksize == 2) KERNEL<2><<<GRID, kThreads, SMEM, s>>>(__VA_ARGS__);   \
+    else KERNEL<0><<<GRID, kThreads, SMEM, s>>>(__VA_ARGS__);                   \
+  } while (0)
+  const int64_t img_bytes = (int64_t)c * oh * ow;
+  if (!out_nchw && (int64_t)n * oh < (1ll << 30)) {
+    const int groups = cp / 16;
+    int gshift = -1;
+    for (int b = 0; b < 12; ++b) if ((1 << b) == groups) gshift = b;
+    I8IE_POOL_KS(maxpool_nhwc_rows_kernel, n * oh, 0, x, y, h, w, c, cp, ksize, stride, oh, ow, gshift);
+  } else if (out_nchw && img_bytes <= 48 * 1024 && img_bytes % 16 == 0 && aligned16(y)) {
+    I8IE_POOL_KS(maxpool_nhwc_to_nchw_image_kernel, n, (size_t)img_bytes, x, y, h, w, c, cp, ksize, stride, oh, ow);
+  } else {
+    const int grid = stream_grid(items, kThreads);
+    I8IE_POOL_KS(maxpool_nhwc_kernel, grid, 0, x, y, n, h, w, c, cp, ksize, stride, oh, ow, out_nchw);
+  }
+#undef I8IE_POOL_KS
   return check_launch("maxpool_nhwc_kernel");
 }
 

@@ -237,6 +237,10 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
   // shape dispatch: the tensor-core kernel needs at least one full 32-byte K step to be worthwhile
   const bool eligible = !tc_disabled() && k >= 32;
   I8IE_REQUIRE(!(impl == 2 && !eligible), "fc_u8: shape not eligible for the tcgen05 kernel");
+  // shape dispatch: a classifier head (<= 16 outputs) is one warp per row, not a 128-row MMA tile
+  if ((impl == 0 || impl == 3) && fc_head_eligible(n_pad, ldx, ldw, ldy, x, w))
+    return launch_fc_head(x, ldx, w, ldw, y, ldy, m, n, k, ep, (cudaStream_t)stream);
+  I8IE_REQUIRE(impl != 3, "fc_u8: shape not eligible for the head kernel (needs n_pad == ldy == 16)");
   if (impl != 1 && eligible) {
     int bn, splits, kb_per;
     tc_fc_config(m, ldy, k, &bn, &splits, &kb_per);

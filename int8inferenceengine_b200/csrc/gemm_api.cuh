@@ -22,6 +22,10 @@ struct GemmGeom {
 int launch_simt_igemm(const GemmGeom& g, const uint8_t* x, const int8_t* w, uint8_t* y,
                       const EpiParams& ep, int zp_in, cudaStream_t stream);
 
+// classifier-head fc (n_pad == 16): one warp per row, see simt_gemm.cu
+bool fc_head_eligible(int n_pad, int ldx, int ldw, int ldy, const void* x, const void* w);
+int launch_fc_head(const uint8_t* x, int ldx, const int8_t* w, int ldw, uint8_t* y, int ldy, int m, int n, int k,
+                   const EpiParams& ep, cudaStream_t stream);
 
 // ---- tcgen05 path (tc_gemm.cu) ---------------------------------------------------------
 bool tc_conv_eligible(const GemmGeom& g);

@@ -128,7 +128,85 @@ __global__ void __launch_bounds__(NT) simt_igemm_kernel(const GemmGeom g, const 
   }
 }
 
+// ---- fc with a handful of outputs (classifier heads: N <= 16) ------------------------------------
+// One block per input row, each warp takes a K slice: a lane reads 16 bytes of the row and the
+// matching 16 bytes of all 16 weight rows (17 independent loads in flight), 64 dp4a.u32.s32, then a
+// transpose-reduce (16 shuffles) leaves output j = lane>>1 in every lane; warps fold through shared
+// memory and lane j of warp 0 runs the fused epilogue. Replaces a 128-row tensor-core tile that
+// would be >90 % padding plus its split-K reduction.
+constexpr int kHeadN = 16;
+constexpr int kHeadWarps = 8;
+
+__global__ void __launch_bounds__(kHeadWarps * 32) fc_head_kernel(const uint8_t* __restrict__ x, int ldx,
+                                                                  const int8_t* __restrict__ w, int ldw,
+                                                                  uint8_t* __restrict__ y, int ldy, int n,
+                                                                  int kvec, const EpiParams ep, int fast) {
+  __shared__ int32_t part[kHeadWarps][kHeadN];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * ldx);
+  int32_t acc[kHeadN];
+#pragma unroll
+  for (int j = 0; j < kHeadN; ++j) acc[j] = 0;
+  for (int v = warp * 32 + lane; v < kvec; v += kHeadWarps * 32) {
+    const uint4 a = __ldg(xr + v);
+    uint4 b[kHeadN];
+#pragma unroll
+    for (int j = 0; j < kHeadN; ++j) b[j] = __ldg(reinterpret_cast<const uint4*>(w + (size_t)j * ldw) + v);
+#pragma unroll
+    for (int j = 0; j < kHeadN; ++j) {
+      int32_t s = acc[j];
+      s = dp4a_u8s8(a.x, b[j].x, s); s = dp4a_u8s8(a.y, b[j].y, s);
+      s = dp4a_u8s8(a.z, b[j].z, s); s = dp4a_u8s8(a.w, b[j].w, s);
+      acc[j] = s;
+    }
+  }
+  // transpose-reduce: after the step with offset o, a lane keeps the half of its values selected by
+  // that lane bit; 8 + 4 + 2 + 1 exchanges, then one plain fold over the last lane bit
+#pragma unroll
+  for (int o = 16, cnt = kHeadN / 2; cnt >= 1; o >>= 1, cnt >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < cnt; ++j) {
+      const int32_t send = up ? acc[j] : acc[j + cnt];
+      const int32_t keep = up ? acc[j + cnt] : acc[j];
+      acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+  // lane holds output index bits (lane>>4 &1)*8 + (lane>>3 &1)*4 + (lane>>2 &1)*2 + (lane>>1 &1) = lane >> 1
+  if ((lane & 1) == 0) part[warp][lane >> 1] = acc[0];
+  __syncthreads();
+  if (warp != 0 || lane >= kHeadN) return;
+  int32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kHeadWarps; ++k) sum += part[k][lane];
+  uint32_t q = (uint32_t)ep.zp_out;   // pad lanes carry the zero point
+  if (lane < n) {
+    int32_t v = sum + __ldg(ep.oc + lane);
+    if (ep.bias_f) v = fc_bias_add(v, __ldg(ep.bias_f + lane));
+    if (ep.acc_out) ep.acc_out[(size_t)m * n + lane] = v;
+    const float zpf = (float)ep.zp_out;
+    q = fast ? requant_u8_fast(v, ep.sa, ep.sb, ep.sc, __frcp_rn(ep.sc), zpf) : requant_u8(v, ep.sa, ep.sb, ep.sc, zpf);
+    if (ep.relu) q = max(q, (uint32_t)ep.zp_out);
+  }
+  y[(size_t)m * ldy + lane] = (uint8_t)q;
+}
+
 }  // namespace
+
+bool fc_head_eligible(int n_pad, int ldx, int ldw, int ldy, const void* x, const void* w) {
+  return n_pad == kHeadN && ldy == kHeadN && ldx % 16 == 0 && ldw % 16 == 0 && ldw >= ldx &&
+         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+}
+
+int launch_fc_head(const uint8_t* x, int ldx, const int8_t* w, int ldw, uint8_t* y, int ldy, int m, int n, int k,
+                   const EpiParams& ep, cudaStream_t stream) {
+  const int kvec = (k + 15) / 16;   // the [k, ldx) tail multiplies zero weight lanes
+  fc_head_kernel<<<m, kHeadWarps * 32, 0, stream>>>(x, ldx, w, ldw, y, ldy, n, kvec, ep,
+                                                    requant_fast_ok(ep.sa, ep.sb, ep.sc) ? 1 : 0);
+  return check_launch("fc_head_kernel");
+}
 
 int launch_simt_igemm(const GemmGeom& g, const uint8_t* x, const int8_t* w, uint8_t* y,
                       const EpiParams& ep, int zp_in, cudaStream_t stream) {

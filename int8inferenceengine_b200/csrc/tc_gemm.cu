@@ -392,7 +392,7 @@ struct Stem2Params {
   const uint8_t* xs;
 };
 
-template <int BN>
+template <int BN, int KH>   // KH > 0: filter height known at compile time (fully unrolled issue loop)
 __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
                                                                const TcParams p, const Stem2Params sp) {
   extern __shared__ uint8_t smem_raw[];
@@ -429,59 +429,84 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
   const uint32_t row_bytes = (uint32_t)sp.wsp * 16;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // weights once
+    // ===== producer: the whole warp walks the tile loop, lane i copies row i of the tile (one
+    // bulk copy each, issued in parallel instead of 15 back-to-back from one thread) =====
+    if (lane == 0) {   // weights once
       ptx::mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
       for (int r = 0; r < sp.kh; ++r) ptx::tma_load_2d(sW + (size_t)r * BN * 64, &tmB, w_full, r * 64, 0);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
-        const int s = it % sp.stages;
-        const uint32_t ph = (it / sp.stages) & 1;
-        if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); break; }
-        const int i0 = 4 * p0;
-        int nrows = sp.hp - i0;
-        if (nrows > rows_per_tile) nrows = rows_per_tile;
-        if (sp.dbg & 4) { ptx::mbar_arrive(&ctl->full[s]); continue; }
-        ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)nrows * row_bytes);
-        uint8_t* st = sA + (size_t)s * a_stage;
-        const uint8_t* src = sp.xs + ((size_t)img * sp.hp + i0) * row_bytes;
-        for (int i = 0; i < nrows; ++i)
-          ptx::bulk_load_1d(st + (size_t)((i & 3) * sp.nsl + (i >> 2)) * 1024, src + (size_t)i * row_bytes, row_bytes,
-                            &ctl->full[s]);
-      }
+    }
+    uint32_t it = 0;
+    bool alive = true;
+    for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++it) {
+      const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
+      const uint32_t s = it % (uint32_t)sp.stages;
+      const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
+      if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+      const int i0 = 4 * p0;
+      int nrows = sp.hp - i0;
+      if (nrows > rows_per_tile) nrows = rows_per_tile;
+      if (sp.dbg & 4) { if (lane == 0) ptx::mbar_arrive(&ctl->full[s]); __syncwarp(); continue; }
+      // the arrival (with the byte count) and the copies may land in any order: the phase cannot
+      // complete before the single arrival, and by then the transaction count is balanced
+      if (lane == 0) ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)nrows * row_bytes);
+      uint8_t* st = sA + (size_t)s * a_stage;
+      const uint8_t* src = sp.xs + ((size_t)img * sp.hp + i0) * row_bytes;
+      for (int i = lane; i < nrows; i += 32)
+        ptx::bulk_load_1d(st + (size_t)((i & 3) * sp.nsl + (i >> 2)) * 1024, src + (size_t)i * row_bytes, row_bytes,
+                          &ctl->full[s]);
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
-      bool alive = ptx::mbar_wait(w_full, 0);
-      if (!alive) atomicCAS(&g_tc_error, 0, 5);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, bph = (it >> 1) & 1;
-        const int s = it % sp.stages;
-        const uint32_t ph = (it / sp.stages) & 1;
-        if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
-        if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * acc_stride<BN>();
-        const uint32_t sa0 = ptx::smem_u32(sA + (size_t)s * a_stage);
-        const uint32_t sw0 = ptx::smem_u32(sW);
-        for (int r = 0; r < sp.kh; ++r) {
-          const uint32_t a_row = sa0 + (uint32_t)((r & 3) * sp.nsl + (r >> 2)) * 1024u;
+    // ===== MMA issuer. The whole warp walks the loop so that every address below is warp-uniform
+    // (descriptor words live in uniform registers, no per-MMA broadcast); lane 0 issues. =====
+    constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // A: no-swizzle K-major, LBO = 16 B (the two K chunks), SBO = 128 B (8-row groups), version 1
+    constexpr uint32_t a_flags = (16u >> 4) << 16, a_hi = (128u >> 4) | (1u << 14);
+    const uint32_t b_hi = ptx::smem_desc_hi<64>();
+    const uint32_t b_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sW));
+    const uint32_t sa_base = ptx::smem_u32(sA);
+    bool alive = ptx::mbar_wait(w_full, 0);
+    if (!alive) atomicCAS(&g_tc_error, 0, 5);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+      const uint32_t s = it % (uint32_t)sp.stages;
+      const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
+      if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
+      if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tbase + buf * acc_stride<BN>();
+      const uint32_t a_lo0 = (((sa_base + s * (uint32_t)a_stage) & 0x3FFFFu) >> 4) | a_flags;
+      if (lane == 0 && !(sp.dbg & 2)) {
+        if (KH > 0) {
+          constexpr int NSL = (KH + 4 + 3) / 4;
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            ptx::mma_i8_ss(d_tmem, ptx::make_smem_desc_nosw(a_row + k * 32, 16, 128),
-                           ptx::make_smem_desc<64>(sw0 + (uint32_t)r * BN * 64 + k * 32), idesc, (r | k) != 0 ? 1u : 0u);
+          for (int r = 0; r < KH; ++r) {
+            constexpr int kDummy = 0; (void)kDummy;
+            const uint32_t a_lo = a_lo0 + (uint32_t)(((r & 3) * NSL + (r >> 2)) * 64);   // 1 KB slots, >> 4
+            const uint32_t b_lo = b_lo0 + (uint32_t)(r * BN * 4);                        // BN x 64 B per filter row
+            ptx::mma_i8_ss_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, r != 0 ? 1u : 0u);
+            ptx::mma_i8_ss_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+          }
+        } else {
+          for (int r = 0; r < sp.kh; ++r) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)(((r & 3) * sp.nsl + (r >> 2)) * 64);
+            const uint32_t b_lo = b_lo0 + (uint32_t)(r * BN * 4);
+            ptx::mma_i8_ss_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, r != 0 ? 1u : 0u);
+            ptx::mma_i8_ss_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
           }
         }
+      }
+      if (lane == 0) {
         ptx::tc_commit(&ctl->empty[s]);
         ptx::tc_commit(&ctl->tmem_full[buf]);
       }
-      if (!alive) {
-        ptx::mbar_arrive(&ctl->tmem_full[0]);
-        ptx::mbar_arrive(&ctl->tmem_full[1]);
-      }
+      __syncwarp();
+    }
+    if (!alive && lane == 0) {
+      ptx::mbar_arrive(&ctl->tmem_full[0]);
+      ptx::mbar_arrive(&ctl->tmem_full[1]);
     }
   } else {
     const int quad = warp & 3;
@@ -589,71 +614,88 @@ __global__ void stem_pack_kernel(const uint8_t* __restrict__ x, uint8_t* __restr
 
 // Same layout, produced straight from the fp32 NCHW image with the input quantise
 // (quantize_utils.cc:44-52) fused in. One thread per superpixel (4 px x 4 lanes = one 128-bit
-// store). VEC2: pad and w even -> the 4 pixels are two aligned float2 per channel plane.
-// FAST: division by the hoisted reciprocal with FMA correction (quant_u8_wrap_fast).
+// store); grid.y = image, so the only per-thread division is a 32-bit one.
+// VEC2: pad and w even -> the 4 pixels are two aligned float2 per channel plane.
+// FAST: packed fp32x2 quantise behind one magnitude test per thread (quant2_fast).
 template <bool VEC2, bool FAST>
 __global__ void __launch_bounds__(256) stem_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs,
-                                                            int n, int c, int h, int w, int pad, int hp, int wsp,
-                                                            float scale, float zpf, uint32_t zp,
+                                                            int c, int h, int w, int pad, int hp, int wsp,
+                                                            float scale, float zpf, uint32_t zp, float fast_lim,
                                                             const float* const* __restrict__ xslot) {
   if (xslot) x = *xslot;   // run-time source address (CUDA-graph replay on a new input buffer)
-  const int64_t total = (int64_t)n * hp * wsp;
-  const float rcp = __frcp_rn(scale);
-  const int64_t plane = (int64_t)h * w;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int sx = (int)(t % wsp);
-    const int y = (int)((t / wsp) % hp);
-    const int img = (int)(t / ((int64_t)wsp * hp));
-    const int row = y - pad;
-    const uint32_t zp4 = zp * 0x01010101u;
-    uint32_t wd[4] = {zp4, zp4, zp4, zp4};
-    if (row >= 0 && row < h) {
-      const int col0 = sx * 4 - pad;
-      const float* src = x + ((int64_t)img * c * h + row) * w + col0;
-      float f[4][4];   // [channel lane][pixel]
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= (uint32_t)(hp * wsp)) return;
+  const int img = blockIdx.y;
+  const int y = (int)(idx / (uint32_t)wsp), sx = (int)(idx - (uint32_t)y * (uint32_t)wsp);
+  const int row = y - pad;
+  const uint32_t zp4 = zp * 0x01010101u;
+  uint32_t wd[4] = {zp4, zp4, zp4, zp4};
+  if (row >= 0 && row < h) {
+    const int64_t plane = (int64_t)h * w;
+    const int col0 = sx * 4 - pad;
+    const float* src = x + ((int64_t)img * c * h + row) * w + col0;
+    float f[4][4];   // [channel lane][pixel]
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
+    for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) f[ch][j] = 0.f;
-      if (VEC2) {
+      for (int j = 0; j < 4; ++j) f[ch][j] = 0.f;
+    if (VEC2) {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < c) {
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < c) {
 #pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-              if (col0 + j >= 0 && col0 + j < w) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(src + ch * plane + j));
-                f[ch][j] = v.x; f[ch][j + 1] = v.y;
-              }
+          for (int j = 0; j < 4; j += 2) {
+            if (col0 + j >= 0 && col0 + j < w) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(src + ch * plane + j));
+              f[ch][j] = v.x; f[ch][j + 1] = v.y;
             }
           }
         }
-      } else {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          if (ch < c)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (col0 + j >= 0 && col0 + j < w) f[ch][j] = __ldg(src + ch * plane + j);
       }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (col0 + j >= 0 && col0 + j < w) {
-          uint32_t v = 0;
+      for (int ch = 0; ch < 4; ++ch)
+        if (ch < c)
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t q = (ch < c) ? (FAST ? quant_u8_wrap_fast(f[ch][j], scale, rcp, zpf)
-                                                : quant_u8_wrap(f[ch][j], scale, zpf))
-                                        : zp;
-            v |= q << (8 * ch);
+          for (int j = 0; j < 4; ++j)
+            if (col0 + j >= 0 && col0 + j < w) f[ch][j] = __ldg(src + ch * plane + j);
+    }
+    int q[4][4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[ch][j] = (int)zp;
+    bool done = false;
+    if (FAST) {
+      float amax = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fabsf(f[ch][j]));
+      if (amax < fast_lim) {
+        const QuantFast2 qc = make_quant_fast2(scale, __frcp_rn(scale), zpf);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < c) {
+            quant2_fast(f[ch][0], f[ch][1], qc, q[ch][0], q[ch][1]);
+            quant2_fast(f[ch][2], f[ch][3], qc, q[ch][2], q[ch][3]);
           }
-          wd[j] = v;
         }
+        done = true;
       }
     }
-    *reinterpret_cast<uint4*>(xs + t * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    if (!done) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        if (ch < c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[ch][j] = (int)quant_u8_wrap(f[ch][j], scale, zpf);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j >= 0 && col0 + j < w) wd[j] = pack_low_bytes(q[0][j], q[1][j], q[2][j], q[3][j]);
   }
+  *reinterpret_cast<uint4*>(xs + (((int64_t)img * hp + y) * wsp + sx) * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
 }
 
 // stem weights: ws[n][r][64], lane j = 4*px + ch
@@ -1030,13 +1072,13 @@ int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, u
 
 int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x, const float* const* xslot,
                            uint8_t* xs, float scale, int zp, cudaStream_t stream) {
-  const int64_t total = (int64_t)g.n * s.hp * s.wsp;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  const dim3 grid((unsigned)((s.hp * s.wsp + 255) / 256), (unsigned)g.n);
   const bool vec2 = (g.pad % 2 == 0) && (g.w % 2 == 0) && (xslot || (reinterpret_cast<uintptr_t>(x) & 7) == 0);
-  const bool fast = quant_fast_ok(scale);
-#define I8IE_STEMQ(V, F) stem_quantize_kernel<V, F><<<blocks, 256, 0, stream>>>( \
-      x, xs, g.n, s.c, g.h, g.w, g.pad, s.hp, s.wsp, scale, (float)zp, (uint32_t)zp, xslot)
+  const float lim = quant_fast_limit(scale);
+  const bool fast = lim > 0.f;
+  I8IE_REQUIRE(g.n <= 65535, "stem quantise: batch %d exceeds the grid.y limit", g.n);
+#define I8IE_STEMQ(V, F) stem_quantize_kernel<V, F><<<grid, 256, 0, stream>>>( \
+      x, xs, s.c, g.h, g.w, g.pad, s.hp, s.wsp, scale, (float)zp, (uint32_t)zp, lim, xslot)
   if (vec2 && fast) I8IE_STEMQ(true, true);
   else if (vec2) I8IE_STEMQ(true, false);
   else if (fast) I8IE_STEMQ(false, true);
@@ -1100,9 +1142,11 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   sp.stages = stages;
   const int smem = w_bytes + stages * a_stage + ctl_bytes + 1024;
   static int attr_smem = 0;
-  auto kern = tc_stem2_kernel<BN>;
+  auto kern = g.kh == 11 ? tc_stem2_kernel<BN, 11> : g.kh == 7 ? tc_stem2_kernel<BN, 7> : tc_stem2_kernel<BN, 0>;
   if (attr_smem < smem) {
-    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
   const int tiles = sp.n_img * sp.pairs;

@@ -195,7 +195,9 @@ def test_maxpool(shape, k, s, out_nchw):
     if out_nchw:
         assert np.array_equal(y.cpu().numpy().reshape(n, c, oh, ow), exp)
     else:
-        assert np.array_equal(y.cpu().numpy().reshape(n, oh, ow, cp)[..., :c], exp.transpose(0, 2, 3, 1))
+        got = y.cpu().numpy().reshape(n, oh, ow, cp)
+        assert np.array_equal(got[..., :c], exp.transpose(0, 2, 3, 1))
+        assert np.all(got[..., c:] == 7)      # pad lanes keep the producer's pad value (its zero point)
 
 
 def test_relu_pool_golden():
