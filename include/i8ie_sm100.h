@@ -76,6 +76,19 @@ I8IE_API int i8ie_quantize_nchw_f32_nhwc_u8_indirect(const float* const* x_slot,
 /* dst[0, nbytes) = (*src_slot)[0, nbytes); nbytes % 16 == 0, both 16-byte aligned. */
 I8IE_API int i8ie_copy_indirect(const void* const* src_slot, void* dst, int64_t nbytes, void* stream);
 
+/* ---- multi-GPU result exchange (no reference counterpart: the reference is single-process) ----
+ * Batch shards are independent; the only exchange is the result. Each rank packs
+ *   chunk = { int64 agree; int32 rows; int32 cols; float logits[rows_cap * cols] }
+ * (agree = rows whose first-maximum argmax equals ref_argmax[r]; ref_argmax may be NULL), ONE
+ * NCCL all-gather moves the chunks, and unpack writes the dense [sum rows, cols] logits in rank
+ * order plus the summed count. chunk bytes = i8ie_top1_chunk_bytes(rows_cap, cols), a multiple
+ * of 16 when rows_cap * cols is a multiple of 4 (pad rows_cap otherwise). */
+I8IE_API int64_t i8ie_top1_chunk_bytes(int rows_cap, int cols);
+I8IE_API int i8ie_top1_pack(const float* logits, const int64_t* ref_argmax, int rows, int cols, void* packed,
+                   void* stream);
+I8IE_API int i8ie_top1_unpack(const void* gathered, int world, int64_t chunk_bytes, float* logits_all,
+                     int64_t* agree_total, void* stream);
+
 /* A5: dequantize(float*, u8*, size, scale, zp), quantize_utils.cc:38-42:
  *   x[i] = (float)((int)q[i] - zp) * scale. Flat, dense. */
 I8IE_API int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, int zp, void* stream);

@@ -18,7 +18,7 @@ SYMBOLS = [
     "i8ie_pack_conv_weight", "i8ie_conv2d_plan_create", "i8ie_conv2d_plan_destroy",
     "i8ie_conv2d_plan_impl", "i8ie_conv2d_u8", "i8ie_conv2d_f32_u8", "i8ie_fc_u8", "i8ie_debug_tc_error",
     "i8ie_quantize_f32_u8_indirect", "i8ie_quantize_nchw_f32_nhwc_u8_indirect", "i8ie_copy_indirect",
-    "i8ie_conv2d_f32_u8_indirect",
+    "i8ie_conv2d_f32_u8_indirect", "i8ie_top1_chunk_bytes", "i8ie_top1_pack", "i8ie_top1_unpack",
 ]
 
 _lib = None
@@ -73,6 +73,10 @@ def load():
     L.i8ie_quantize_f32_u8_indirect.argtypes = [vp, vp, i64, f, i, vp]
     L.i8ie_quantize_nchw_f32_nhwc_u8_indirect.argtypes = [vp, vp, i, i, i, i, i, f, i, vp]
     L.i8ie_copy_indirect.argtypes = [vp, vp, i64, vp]
+    L.i8ie_top1_chunk_bytes.argtypes = [i, i]
+    L.i8ie_top1_chunk_bytes.restype = i64
+    L.i8ie_top1_pack.argtypes = [vp, vp, i, i, vp, vp]
+    L.i8ie_top1_unpack.argtypes = [vp, i, i64, vp, vp, vp]
     L.i8ie_debug_tc_error.argtypes = [i]
     _lib = L
     return L

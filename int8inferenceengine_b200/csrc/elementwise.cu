@@ -313,6 +313,66 @@ __global__ void __launch_bounds__(kThreads) copy_indirect_kernel(const uint4* co
     st_stream_u4(dst + v, ld_stream_u4(src + v));
 }
 
+// ---- multi-GPU result exchange: pack [agreement count | logits] for ONE all-gather -----------
+// chunk layout (bytes): int64 agree | int32 rows | int32 cols | rows_cap*cols fp32 logits
+struct ExchangeHeader {
+  long long agree;
+  int rows, cols;
+};
+
+// One block. Row r: argmax (first maximum, like numpy/torch) compared with ref_argmax[r]; the
+// logits are copied behind the header.
+__global__ void __launch_bounds__(1024) top1_pack_kernel(const float* __restrict__ logits,
+                                                         const long long* __restrict__ ref_argmax, int rows,
+                                                         int cols, uint8_t* __restrict__ packed) {
+  __shared__ int s_cnt[32];
+  int cnt = 0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float* row = logits + (size_t)r * cols;
+    int best = 0;
+    float bv = row[0];
+    for (int j = 1; j < cols; ++j) {
+      const float v = row[j];
+      if (v > bv) { bv = v; best = j; }
+    }
+    if (ref_argmax && (long long)best == ref_argmax[r]) ++cnt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    cnt = (threadIdx.x < (blockDim.x >> 5)) ? s_cnt[threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (threadIdx.x == 0) {
+      ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(packed);
+      h->agree = cnt; h->rows = rows; h->cols = cols;
+    }
+  }
+  float* dst = reinterpret_cast<float*>(packed + sizeof(ExchangeHeader));
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) dst[i] = logits[i];
+}
+
+// One block. Gathered chunks (rank order, `chunk_bytes` apart) -> dense logits of all ranks in
+// rank order (only each rank's valid rows) + the summed agreement count.
+__global__ void __launch_bounds__(1024) top1_unpack_kernel(const uint8_t* __restrict__ gathered, int world,
+                                                           long long chunk_bytes, float* __restrict__ logits_all,
+                                                           long long* __restrict__ agree_total) {
+  long long total = 0;
+  int row0 = 0;
+  for (int k = 0; k < world; ++k) {
+    const uint8_t* chunk = gathered + (size_t)k * chunk_bytes;
+    const ExchangeHeader h = *reinterpret_cast<const ExchangeHeader*>(chunk);
+    const float* src = reinterpret_cast<const float*>(chunk + sizeof(ExchangeHeader));
+    float* dst = logits_all + (size_t)row0 * h.cols;
+    for (int i = threadIdx.x; i < h.rows * h.cols; i += blockDim.x) dst[i] = src[i];
+    total += h.agree;
+    row0 += h.rows;
+  }
+  if (threadIdx.x == 0) *agree_total = total;
+}
+
 // ---- A11 max_pool2d<u8>, NHWC --------------------------------------------------
 // Byte-wise unsigned max of 16 channels, kept as even/odd bytes in u16x2 lanes: one tap word
 // costs 2 PRMT + 2 VIMNMX.U16x2 (the __vmaxu4 intrinsic is a 7-instruction emulation on sm_100).
@@ -653,6 +713,28 @@ int i8ie_downscale_s32_u8(const int32_t* acc, uint8_t* y, int64_t n, float sa, f
   else
     downscale_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
   return check_launch("downscale_flat_kernel");
+}
+
+int64_t i8ie_top1_chunk_bytes(int rows_cap, int cols) {
+  return (int64_t)sizeof(ExchangeHeader) + (int64_t)rows_cap * cols * 4;
+}
+
+int i8ie_top1_pack(const float* logits, const int64_t* ref_argmax, int rows, int cols, void* packed, void* stream) {
+  I8IE_REQUIRE(logits && packed && rows >= 0 && cols > 0 && aligned16(packed), "top1_pack: bad arguments");
+  top1_pack_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(ref_argmax), rows,
+                                                       cols, reinterpret_cast<uint8_t*>(packed));
+  return check_launch("top1_pack_kernel");
+}
+
+int i8ie_top1_unpack(const void* gathered, int world, int64_t chunk_bytes, float* logits_all, int64_t* agree_total,
+                     void* stream) {
+  I8IE_REQUIRE(gathered && logits_all && agree_total && world > 0 && chunk_bytes >= (int64_t)sizeof(ExchangeHeader) &&
+                   chunk_bytes % 16 == 0 && aligned16(gathered),
+               "top1_unpack: bad arguments");
+  top1_unpack_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(gathered), world,
+                                                         (long long)chunk_bytes, logits_all,
+                                                         reinterpret_cast<long long*>(agree_total));
+  return check_launch("top1_unpack_kernel");
 }
 
 int64_t i8ie_minmax_workspace_bytes(void) { return (int64_t)sizeof(MinMaxWs); }

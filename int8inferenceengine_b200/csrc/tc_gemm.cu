@@ -58,6 +58,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant (warp % 4), alternating 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
+// stem kernel: its K is tiny (22 MMAs per tile), so the fp32 epilogue is the longest stage; with two
+// warps per sub-partition it runs latency-bound, four warps per sub-partition hide the dependent chains
+constexpr int kStemEpiWarps = 16;
+constexpr int kStemThreads = 64 + 32 * kStemEpiWarps;
 constexpr int kMaxStages = 16;
 
 template <int BN>
@@ -94,7 +98,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // [fc float bias], requantise, [relu], packed u8 store. m < 0: row is padding (nothing stored).
 // Two warps share each TMEM lane quadrant and take alternate 32-column chunks (`half`).
 // `s_oc` / `s_bias` are shared-memory addresses of this tile's staged per-channel terms.
-template <int BN>
+template <int BN, int NSUB = kEpiWarps / 4>   // NSUB warps share a quadrant and take every NSUB-th chunk
 __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, long long m, int n0,
                                              uint32_t s_oc, uint32_t s_bias, const int32_t* corr, float rcp,
                                              int half) {
@@ -104,7 +108,7 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
   const RequantFast2 rq = make_requant_fast2(sa, sb, sc, rcp, zpf);
   uint8_t* yrow = p.y + (size_t)(m < 0 ? 0 : m) * p.out_cp;
 #pragma unroll 1
-  for (int c0 = half * 32; c0 < BN; c0 += 64) {
+  for (int c0 = half * 32; c0 < BN; c0 += 32 * NSUB) {
     if (n0 + c0 >= p.out_cp) break;   // warp-uniform
     uint32_t v[32];
     ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
@@ -393,7 +397,7 @@ struct Stem2Params {
 };
 
 template <int BN, int KH>   // KH > 0: filter height known at compile time (fully unrolled issue loop)
-__global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
                                                                const TcParams p, const Stem2Params sp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
     ptx::mbar_init(w_full, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
-      ptx::mbar_init(&ctl->tmem_empty[b], kEpiWarps);
+      ptx::mbar_init(&ctl->tmem_empty[b], kStemEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -478,7 +482,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
       ptx::tc_fence_after();
       const uint32_t d_tmem = tbase + buf * acc_stride<BN>();
       const uint32_t a_lo0 = (((sa_base + s * (uint32_t)a_stage) & 0x3FFFFu) >> 4) | a_flags;
-      if (lane == 0 && !(sp.dbg & 2)) {
+      const bool leader = ptx::elect_one_sync();
+      if (leader && !(sp.dbg & 2)) {
         if (KH > 0) {
           constexpr int NSL = (KH + 4 + 3) / 4;
 #pragma unroll
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
           }
         }
       }
-      if (lane == 0) {
+      if (leader) {
         ptx::tc_commit(&ctl->empty[s]);
         ptx::tc_commit(&ctl->tmem_full[buf]);
       }
@@ -513,11 +518,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
     const int et = threadIdx.x - 64;
     const float rcp = __frcp_rn(p.ep.sc);
     // per-channel offsets are the same for every tile (single N tile)
-    for (int j = et; j < BN; j += 32 * kEpiWarps) {
+    for (int j = et; j < BN; j += 32 * kStemEpiWarps) {
       ctl->oc[0][j] = (j < p.N) ? __ldg(p.ep.oc + j) : 0;
       ctl->bias[0][j] = 0.f;
     }
-    epi_bar_sync();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kStemEpiWarps) : "memory");
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1, bph = (it >> 1) & 1;
@@ -531,11 +536,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_stem2_kernel(const __grid_cons
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
       if (!(sp.dbg & 1)) {
-        epilogue_row<BN>(p, t_row, (ok && !(sp.dbg & 8)) ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]),
-                         ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2);
+        epilogue_row<BN, kStemEpiWarps / 4>(p, t_row, (ok && !(sp.dbg & 8)) ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]),
+                                            ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2);
         // output pitch wider than the N tile (e.g. 96 channels stored at pitch 128): the pad lanes
         // carry the zero point; written by the warp of each pair that had fewer chunks
-        if (BN < p.out_cp && ((warp - 2) >> 2) == ((BN / 32) & 1) && ok && m >= 0) {
+        if (BN < p.out_cp && ((warp - 2) >> 2) == ((BN / 32) % (kStemEpiWarps / 4)) && ok && m >= 0) {
           const uint32_t z4 = (uint32_t)p.ep.zp_out * 0x01010101u;
           for (int c = BN; c < p.out_cp; c += 16)
             *reinterpret_cast<uint4*>(p.y + (size_t)m * p.out_cp + c) = make_uint4(z4, z4, z4, z4);
@@ -1133,6 +1138,7 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   sp.xs = xs;
   sp.dbg = 0;
   if (const char* e = std::getenv("I8IE_STEM2_DBG")) sp.dbg = std::atoi(e);
+
   const int w_bytes = g.kh * BN * 64;
   const int a_stage = 4 * sp.nsl * 1024;
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
@@ -1151,7 +1157,7 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   }
   const int tiles = sp.n_img * sp.pairs;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, smem, stream>>>(tmB, p, sp);
+  kern<<<grid, kStemThreads, smem, stream>>>(tmB, p, sp);
   return check_launch("tc_stem2_kernel");
 }
 

@@ -52,3 +52,54 @@ def reduce_count(local_count: int, device="cpu") -> int:
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return int(t.item())
+
+
+class ResultExchange:
+    """Fused result exchange of one sharded step on GPUs: one pack kernel (top-1 agreement
+    count + logits behind a 16-byte header), ONE `all_gather_into_tensor` over NCCL, one unpack
+    kernel. Replaces all-gather(logits) + all-reduce(count) and the handful of tiny torch kernels
+    that computed the count; handles uneven shards (each chunk carries its row count).
+    CUDA only — the kernels live in libi8ie_sm100.so (include/i8ie_sm100.h, i8ie_top1_*)."""
+
+    def __init__(self, global_batch: int, cols: int, device):
+        from . import _lib
+        self._L = _lib.load()
+        self._check = _lib.check
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.global_batch, self.cols = int(global_batch), int(cols)
+        spans = [shard_range(global_batch, r, self.world) for r in range(self.world)]
+        self.rows = spans[self.rank][1] - spans[self.rank][0]
+        cap = max(hi - lo for lo, hi in spans)
+        while (cap * cols) % 4:
+            cap += 1
+        self.chunk = int(self._L.i8ie_top1_chunk_bytes(cap, cols))
+        self.packed = torch.zeros(self.chunk, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=device)
+        self.logits_all = torch.empty(self.global_batch, cols, dtype=torch.float32, device=device)
+        self.agree = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def __call__(self, local_logits: torch.Tensor, ref_argmax: torch.Tensor | None = None):
+        """local_logits: [rows, cols] fp32 CUDA (contiguous); ref_argmax: [rows] int64 CUDA or None.
+        Returns (logits of all ranks [global_batch, cols], agreement count tensor [1] int64) —
+        static buffers, valid until the next call; everything is stream-ordered, nothing syncs."""
+        if not local_logits.is_cuda or local_logits.dtype != torch.float32 or not local_logits.is_contiguous():
+            raise ValueError("ResultExchange needs a contiguous fp32 CUDA tensor")
+        if tuple(local_logits.shape) != (self.rows, self.cols):
+            raise ValueError(f"expected logits of shape {(self.rows, self.cols)}, got {tuple(local_logits.shape)}")
+        st = torch.cuda.current_stream().cuda_stream
+        ref_ptr = None
+        if ref_argmax is not None:
+            if ref_argmax.dtype != torch.int64 or ref_argmax.numel() != self.rows or not ref_argmax.is_cuda:
+                raise ValueError("ref_argmax must be int64 CUDA with one entry per local row")
+            ref_ptr = ref_argmax.data_ptr()
+        self._check(self._L.i8ie_top1_pack(local_logits.data_ptr(), ref_ptr, self.rows, self.cols,
+                                           self.packed.data_ptr(), st), "top1_pack")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.packed)
+            src = self.gathered
+        else:
+            src = self.packed
+        self._check(self._L.i8ie_top1_unpack(src.data_ptr(), self.world, self.chunk, self.logits_all.data_ptr(),
+                                             self.agree.data_ptr(), st), "top1_unpack")
+        return self.logits_all, self.agree

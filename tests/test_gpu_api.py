@@ -150,3 +150,42 @@ def test_error_paths():
         L2(i8ie.quantize(i8ie.tensor(rnd((2, 4))), 0.025, 127))   # u8 forward before convert
     with pytest.raises(RuntimeError):
         i8ie.Conv2d(1, 1, 3, stride=0)       # conv2d.h:12-14
+
+
+def test_result_exchange_pack_unpack():
+    """The fused multi-GPU result exchange (i8ie_top1_pack / _unpack): agreement count + logits
+    in one chunk per rank; world 1 through ResultExchange, several ranks by hand-assembling the
+    gathered buffer (uneven shards included)."""
+    import torch
+    from int8inferenceengine_b200 import _lib
+    from int8inferenceengine_b200.sharding import ResultExchange, shard_range
+    L = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(5)
+    gb, c = 10, 10
+    logits = rng.normal(size=(gb, c)).astype(np.float32)
+    logits[3, 2] = logits[3, 7] = logits[3].max() + 1.0         # tie: the first maximum wins
+    ref = logits.argmax(1).astype(np.int64)
+    ref[[1, 4]] = (ref[[1, 4]] + 1) % c                          # two disagreements
+    ex = ResultExchange(gb, c, torch.device("cuda"))
+    allg, agree = ex(torch.from_numpy(logits).cuda(), torch.from_numpy(ref).cuda())
+    assert np.array_equal(allg.cpu().numpy(), logits) and int(agree.item()) == gb - 2
+    allg, agree = ex(torch.from_numpy(logits).cuda(), None)
+    assert int(agree.item()) == 0
+    # three ranks, 10 rows -> shards of 4 / 3 / 3
+    world = 3
+    cap = 4
+    chunk = int(L.i8ie_top1_chunk_bytes(cap, c))
+    assert chunk % 16 == 0
+    gathered = torch.zeros(world * chunk, dtype=torch.uint8, device="cuda")
+    want = 0
+    for r in range(world):
+        lo, hi = shard_range(gb, r, world)
+        part = torch.from_numpy(logits[lo:hi].copy()).cuda()
+        rf = torch.from_numpy(ref[lo:hi].copy()).cuda()
+        assert L.i8ie_top1_pack(part.data_ptr(), rf.data_ptr(), hi - lo, c, gathered.data_ptr() + r * chunk, st) == 0
+        want += int((logits[lo:hi].argmax(1) == ref[lo:hi]).sum())
+    out = torch.empty(gb, c, dtype=torch.float32, device="cuda")
+    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert L.i8ie_top1_unpack(gathered.data_ptr(), world, chunk, out.data_ptr(), tot.data_ptr(), st) == 0
+    assert np.array_equal(out.cpu().numpy(), logits) and int(tot.item()) == want == gb - 2

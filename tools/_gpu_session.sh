@@ -1,12 +1,11 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-tail -15 gpurun_out/pytest_gpu.log
-for d in 0 1 2 3 7; do echo "DBG=$d"; I8IE_STEM2_DBG=$d python tools/step_trace.py 2>&1 | tail -18 | sed -n 2,4p; done
-python tools/step_trace.py > gpurun_out/step_trace_b100.txt 2>&1; cat gpurun_out/step_trace_b100.txt | tail -19
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "n2 rc=$?"
+tail -2 gpurun_out/bench_n2.err
 python - <<'PY'
 import json
-j=json.load(open('gpurun_out/bench.json'))
-print(j['value'], j['ms_per_step'], j['e2e']['value'])
-print(j['hbm_kernels'])
+for f in ['gpurun_out/bench_n2.json']:
+    j=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, j['value'], j['ms_per_step'], j['e2e']['value'], j['config']['per_gpu_batch'])
 PY
+python bench.py --batch 500 --steps 30 --no-cpu-baseline --no-hbm-kernels 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('b500 1gpu', j['value'], j['ms_per_step'])"
