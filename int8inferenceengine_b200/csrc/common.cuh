@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/i8ie_sm100.h"
@@ -53,6 +54,33 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// Kernels of the forward chain are launched with programmatic stream serialisation: a kernel may
+// become resident while its predecessor drains, run its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch), and must call pdl_wait() before its first global-memory access — that
+// returns once the predecessor grid has completed and its writes are visible. Every kernel
+// launched through launch_pdl() calls pdl_launch_dependents() first thing and pdl_wait() before
+// touching global memory, so dependencies stay transitive. Opt-in with I8IE_PDL=1.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline int pdl_enabled() {   // measured on B200: no gain for this chain (kernels are drain/fill bound), so opt-in
+  static const int on = std::getenv("I8IE_PDL") != nullptr ? 1 : 0;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through check_launch()
 }
 
 // ---- the reference's arithmetic, restated with explicitly-rounded intrinsics ---

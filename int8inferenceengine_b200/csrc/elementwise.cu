@@ -32,6 +32,36 @@ inline int stream_grid(int64_t work_items, int per_block) {
   return (int)blocks;
 }
 
+// Persistent grid-stride kernels: exactly as many blocks as can be resident at once (occupancy of
+// THIS kernel x SM count), so the grid-stride loop has no partial last wave.
+template <typename K>
+inline int resident_grid(K kernel, int64_t work_items, int per_block) {
+  // tiny pointer-keyed cache (kernels with identical signatures share this instantiation)
+  static std::atomic<const void*> keys[16];
+  static std::atomic<int> vals[16];
+  const void* key = reinterpret_cast<const void*>(kernel);
+  int per_sm = 0;
+  for (int i = 0; i < 16; ++i) {
+    const void* k = keys[i].load(std::memory_order_acquire);
+    if (k == key) { per_sm = vals[i].load(std::memory_order_relaxed); break; }
+    if (k == nullptr) {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0) != cudaSuccess || v < 1) v = 4;
+      per_sm = v;
+      const void* expect = nullptr;
+      vals[i].store(v, std::memory_order_relaxed);
+      if (keys[i].compare_exchange_strong(expect, key, std::memory_order_release)) break;
+      if (expect == key) break;
+    }
+  }
+  if (per_sm == 0) per_sm = 4;
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
 
@@ -98,6 +128,8 @@ __global__ void __launch_bounds__(kThreads) quantize_flat_kernel(const float* __
 __global__ void __launch_bounds__(kThreads) quantize_nchw_nhwc_kernel(
     const float* __restrict__ x, uint8_t* __restrict__ q, int n, int c, int hw, int cp, float scale,
     float zpf, uint32_t zpb, const float* const* __restrict__ xslot) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (xslot) x = *xslot;
   const int groups = cp >> 4;
   const int64_t total = (int64_t)n * hw * groups;
@@ -162,6 +194,8 @@ __global__ void __launch_bounds__(kThreads) dequantize_flat_kernel(const uint8_t
 
 __global__ void dequantize_rows_kernel(const uint8_t* __restrict__ q, float* __restrict__ x, int rows,
                                        int cols, int pitch, float scale, int zp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = (int64_t)rows * cols;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -425,6 +459,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_nhwc_rows_kernel(const uint8
                                                                      uint8_t* __restrict__ y, int h, int w,
                                                                      int c, int cp, int ks_rt, int st, int oh,
                                                                      int ow, int gshift) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = cp >> 4;
   const int img = blockIdx.x / oh, oy = blockIdx.x - img * oh;
   const uint8_t* xrow = x + ((int64_t)img * h + (int64_t)oy * st) * w * cp;
@@ -445,6 +481,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_nhwc_to_nchw_image_kernel(co
                                                                               int w, int c, int cp, int ks_rt,
                                                                               int st, int oh, int ow) {
   extern __shared__ __align__(16) uint8_t s_out[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = (c + 15) >> 4;   // only groups holding real channels
   const int img = blockIdx.x, plane = oh * ow;
   const uint8_t* ximg = x + (int64_t)img * h * w * cp;
@@ -471,6 +509,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_nhwc_kernel(const uint8_t* _
                                                                 uint8_t* __restrict__ y, int n, int h,
                                                                 int w, int c, int cp, int ks_rt, int st,
                                                                 int oh, int ow, int out_nchw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = cp >> 4;
   const int64_t total = (int64_t)n * oh * ow * groups;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -636,12 +676,13 @@ static int quantize_flat(const float* x, const float* const* xslot, uint8_t* q, 
   I8IE_REQUIRE(n >= 0 && zp >= 0 && zp <= 255, "quantize: bad n/zp");
   if (n == 0) return I8IE_OK;
   const int vec = (xslot || aligned16(x)) && aligned4(q);
-  const int grid = stream_grid((n + 3) / 4, kThreads * kU);
   const float lim = quant_fast_limit(scale);
   if (lim > 0.f)
-    quantize_flat_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot, lim);
+    quantize_flat_kernel<true><<<resident_grid(quantize_flat_kernel<true>, (n + 3) / 4, kThreads * kU), kThreads, 0,
+                                 (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot, lim);
   else
-    quantize_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot, 0.f);
+    quantize_flat_kernel<false><<<resident_grid(quantize_flat_kernel<false>, (n + 3) / 4, kThreads * kU), kThreads, 0,
+                                  (cudaStream_t)stream>>>(x, q, n, scale, (float)zp, vec, xslot, 0.f);
   return check_launch("quantize_flat_kernel");
 }
 
@@ -668,8 +709,8 @@ static int quantize_nhwc(const float* x, const float* const* xslot, uint8_t* q, 
   I8IE_REQUIRE(cp % 16 == 0 && cp >= c && zp >= 0 && zp <= 255 && aligned16(q), "quantize_nhwc: bad cp/zp/alignment");
   const int64_t items = (int64_t)n * h * w * (cp / 16);
   if (items == 0) return I8IE_OK;
-  quantize_nchw_nhwc_kernel<<<stream_grid(items, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      x, q, n, c, h * w, cp, scale, (float)zp, (uint32_t)zp, xslot);
+  launch_pdl(quantize_nchw_nhwc_kernel, dim3(stream_grid(items, kThreads)), dim3(kThreads), 0, (cudaStream_t)stream,
+             x, q, n, c, h * w, cp, scale, (float)zp, (uint32_t)zp, xslot);
   return check_launch("quantize_nchw_nhwc_kernel");
 }
 
@@ -688,8 +729,8 @@ int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, i
   I8IE_REQUIRE(n >= 0, "dequantize: bad n");
   if (n == 0) return I8IE_OK;
   const int vec = aligned16(x) && aligned4(q) && zp >= 0 && zp <= 255;
-  dequantize_flat_kernel<<<stream_grid((n + 3) / 4, kThreads * kUD), kThreads, 0, (cudaStream_t)stream>>>(
-      q, x, n, scale, zp, vec);
+  dequantize_flat_kernel<<<resident_grid(dequantize_flat_kernel, (n + 3) / 4, kThreads * kUD), kThreads, 0,
+                           (cudaStream_t)stream>>>(q, x, n, scale, zp, vec);
   return check_launch("dequantize_flat_kernel");
 }
 
@@ -697,8 +738,8 @@ int i8ie_dequantize_rows_u8_f32(const uint8_t* q, float* x, int rows, int cols, 
                                 int zp, void* stream) {
   I8IE_REQUIRE(rows >= 0 && cols >= 0 && pitch >= cols, "dequantize_rows: bad shape");
   if ((int64_t)rows * cols == 0) return I8IE_OK;
-  dequantize_rows_kernel<<<stream_grid((int64_t)rows * cols, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      q, x, rows, cols, pitch, scale, zp);
+  launch_pdl(dequantize_rows_kernel, dim3(stream_grid((int64_t)rows * cols, kThreads)), dim3(kThreads), 0,
+             (cudaStream_t)stream, q, x, rows, cols, pitch, scale, zp);
   return check_launch("dequantize_rows_kernel");
 }
 
@@ -707,11 +748,12 @@ int i8ie_downscale_s32_u8(const int32_t* acc, uint8_t* y, int64_t n, float sa, f
   I8IE_REQUIRE(n >= 0, "downscale: bad n");
   if (n == 0) return I8IE_OK;
   const int vec = aligned16(acc) && aligned4(y);
-  const int grid = stream_grid((n + 3) / 4, kThreads * kU);
   if (requant_fast_ok(sa, sb, sc))
-    downscale_flat_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
+    downscale_flat_kernel<true><<<resident_grid(downscale_flat_kernel<true>, (n + 3) / 4, kThreads * kU), kThreads, 0,
+                                  (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
   else
-    downscale_flat_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
+    downscale_flat_kernel<false><<<resident_grid(downscale_flat_kernel<false>, (n + 3) / 4, kThreads * kU), kThreads, 0,
+                                   (cudaStream_t)stream>>>(acc, y, n, sa, sb, sc, (float)zp_c, vec);
   return check_launch("downscale_flat_kernel");
 }
 
@@ -741,7 +783,7 @@ int64_t i8ie_minmax_workspace_bytes(void) { return (int64_t)sizeof(MinMaxWs); }
 
 int i8ie_minmax_f32(const float* x, int64_t n, float* out2, void* workspace, void* stream) {
   I8IE_REQUIRE(n > 0 && workspace != nullptr, "minmax: n must be > 0 and workspace non-null");
-  int grid = stream_grid((n + 15) / 16, kThreads);
+  int grid = resident_grid(minmax_kernel, (n + 15) / 16, kThreads);
   if (grid > kMinMaxMaxBlocks) grid = kMinMaxMaxBlocks;
   minmax_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, n, out2, (MinMaxWs*)workspace, aligned16(x));
   return check_launch("minmax_kernel");
@@ -763,7 +805,7 @@ int i8ie_relu_u8(const uint8_t* x, uint8_t* y, int64_t n, int zp, void* stream) 
   I8IE_REQUIRE(n >= 0 && zp >= 0 && zp <= 255, "relu: bad n/zp");
   if (n == 0) return I8IE_OK;
   const uint32_t z = (uint32_t)zp;
-  relu_flat_kernel<<<stream_grid((n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+  relu_flat_kernel<<<resident_grid(relu_flat_kernel, (n + 15) / 16, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       x, y, n, z | (z << 8) | (z << 16) | (z << 24), aligned16(x) && aligned16(y));
   return check_launch("relu_flat_kernel");
 }
@@ -777,11 +819,11 @@ int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int 
   const int64_t items = (int64_t)n * oh * ow * (cp / 16);
   if (items == 0) return I8IE_OK;
   cudaStream_t s = (cudaStream_t)stream;
-#define I8IE_POOL_KS(KERNEL, GRID, SMEM, ...)                                   \
-  do {                                                                          \
-    if (ksize == 3) KERNEL<3><<<GRID, kThreads, SMEM, s>>>(__VA_ARGS__);        \
-    else if (ksize == 2) KERNEL<2><<<GRID, kThreads, SMEM, s>>>(__VA_ARGS__);   \
-    else KERNEL<0><<<GRID, kThreads, SMEM, s>>>(__VA_ARGS__);                   \
+#define I8IE_POOL_KS(KERNEL, GRID, SMEM, ...)                                                     \
+  do {                                                                                            \
+    if (ksize == 3) launch_pdl(KERNEL<3>, dim3(GRID), dim3(kThreads), SMEM, s, __VA_ARGS__);       \
+    else if (ksize == 2) launch_pdl(KERNEL<2>, dim3(GRID), dim3(kThreads), SMEM, s, __VA_ARGS__);  \
+    else launch_pdl(KERNEL<0>, dim3(GRID), dim3(kThreads), SMEM, s, __VA_ARGS__);                  \
   } while (0)
   const int64_t img_bytes = (int64_t)c * oh * ow;
   if (!out_nchw && (int64_t)n * oh < (1ll << 30)) {

@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(NT) simt_igemm_kernel(const GemmGeom g, const 
                                                        const uint32_t zp_in4) {
   __shared__ uint4 sA[2][BM];
   __shared__ uint4 sB[2][BN];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) fc_head_kernel(const uint8_t*
                                                                   uint8_t* __restrict__ y, int ldy, int n,
                                                                   int kvec, const EpiParams ep, int fast) {
   __shared__ int32_t part[kHeadWarps][kHeadN];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m = blockIdx.x;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)m * ldx);
@@ -203,8 +207,8 @@ bool fc_head_eligible(int n_pad, int ldx, int ldw, int ldy, const void* x, const
 int launch_fc_head(const uint8_t* x, int ldx, const int8_t* w, int ldw, uint8_t* y, int ldy, int m, int n, int k,
                    const EpiParams& ep, cudaStream_t stream) {
   const int kvec = (k + 15) / 16;   // the [k, ldx) tail multiplies zero weight lanes
-  fc_head_kernel<<<m, kHeadWarps * 32, 0, stream>>>(x, ldx, w, ldw, y, ldy, n, kvec, ep,
-                                                    requant_fast_ok(ep.sa, ep.sb, ep.sc) ? 1 : 0);
+  launch_pdl(fc_head_kernel, dim3(m), dim3(kHeadWarps * 32), 0, stream, x, ldx, w, ldw, y, ldy, n, kvec, ep,
+             requant_fast_ok(ep.sa, ep.sb, ep.sc) ? 1 : 0);
   return check_launch("fc_head_kernel");
 }
 
@@ -212,7 +216,7 @@ int launch_simt_igemm(const GemmGeom& g, const uint8_t* x, const int8_t* w, uint
                       const EpiParams& ep, int zp_in, cudaStream_t stream) {
   const uint32_t z = (uint32_t)(zp_in & 0xff);
   dim3 grid((g.M + BM - 1) / BM, (g.out_cp + BN - 1) / BN);
-  simt_igemm_kernel<<<grid, NT, 0, stream>>>(g, x, w, y, ep, z | (z << 8) | (z << 16) | (z << 24));
+  launch_pdl(simt_igemm_kernel, grid, dim3(NT), 0, stream, g, x, w, y, ep, z | (z << 8) | (z << 16) | (z << 24));
   return check_launch("simt_igemm_kernel");
 }
 

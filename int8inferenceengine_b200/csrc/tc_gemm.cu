@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kSubA = BM * BK, kSubB = BN * BK;
   constexpr uint32_t NACC = num_acc<BN>();
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     // ===== TMA producer: runs ahead across tile boundaries, the ring never drains =====
@@ -400,6 +402,7 @@ template <int BN, int KH>   // KH > 0: filter height known at compile time (full
 __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
                                                                const TcParams p, const Stem2Params sp) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int w_bytes = sp.kh * BN * 64;          // resident weights, one [BN x 64 B] SW64 tile per filter row
   const int a_stage = 4 * sp.nsl * 1024;
@@ -429,6 +432,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
+  pdl_wait();
   const int rows_per_tile = sp.kh + 4;
   const uint32_t row_bytes = (uint32_t)sp.wsp * 16;
 
@@ -627,6 +631,8 @@ __global__ void __launch_bounds__(256) stem_quantize_kernel(const float* __restr
                                                             int c, int h, int w, int pad, int hp, int wsp,
                                                             float scale, float zpf, uint32_t zp, float fast_lim,
                                                             const float* const* __restrict__ xslot) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (xslot) x = *xslot;   // run-time source address (CUDA-graph replay on a new input buffer)
   const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
   if (idx >= (uint32_t)(hp * wsp)) return;
@@ -722,6 +728,8 @@ __global__ void stem_weight_kernel(const int8_t* __restrict__ wp, int8_t* __rest
 __global__ void __launch_bounds__(256) fc_splitk_reduce_kernel(const int32_t* __restrict__ ws, int splits, int M,
                                                                int N, int ws_ld, int ldy, uint8_t* __restrict__ y,
                                                                const EpiParams ep, int fast) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int quads = ldy >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * quads) return;
@@ -850,7 +858,7 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
 
@@ -1040,8 +1048,8 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   rc = launch_bk<0>(128, bn, tmA, tmB, p, stream);
   if (rc != I8IE_OK) return rc;
   const long long threads = (long long)m * (ldy / 4);
-  fc_splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(p.ws, p.splits, m, n, p.ws_ld, ldy, y,
-                                                                              ep, p.fast_requant);
+  launch_pdl(fc_splitk_reduce_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, p.ws, p.splits, m,
+             n, p.ws_ld, ldy, y, ep, p.fast_requant);
   return check_launch("fc_splitk_reduce_kernel");
 }
 
@@ -1082,7 +1090,7 @@ int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x,
   const float lim = quant_fast_limit(scale);
   const bool fast = lim > 0.f;
   I8IE_REQUIRE(g.n <= 65535, "stem quantise: batch %d exceeds the grid.y limit", g.n);
-#define I8IE_STEMQ(V, F) stem_quantize_kernel<V, F><<<grid, 256, 0, stream>>>( \
+#define I8IE_STEMQ(V, F) launch_pdl(stem_quantize_kernel<V, F>, grid, dim3(256), 0, stream, \
       x, xs, s.c, g.h, g.w, g.pad, s.hp, s.wsp, scale, (float)zp, (uint32_t)zp, lim, xslot)
   if (vec2 && fast) I8IE_STEMQ(true, true);
   else if (vec2) I8IE_STEMQ(true, false);
@@ -1157,7 +1165,7 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   }
   const int tiles = sp.n_img * sp.pairs;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kStemThreads, smem, stream>>>(tmB, p, sp);
+  launch_pdl(kern, dim3(grid), dim3(kStemThreads), (size_t)smem, stream, tmB, p, sp);
   return check_launch("tc_stem2_kernel");
 }
 

@@ -1,11 +1,8 @@
 cd $GRAFT_REPO_ROOT
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "n2 rc=$?"
-tail -2 gpurun_out/bench_n2.err
-python - <<'PY'
-import json
-for f in ['gpurun_out/bench_n2.json']:
-    j=json.loads(open(f).read().strip().splitlines()[-1])
-    print(f, j['value'], j['ms_per_step'], j['e2e']['value'], j['config']['per_gpu_batch'])
-PY
-python bench.py --batch 500 --steps 30 --no-cpu-baseline --no-hbm-kernels 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('b500 1gpu', j['value'], j['ms_per_step'])"
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python tools/step_trace.py > gpurun_out/step_trace_b100.txt 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-hbm-kernels --profiler-range > gpurun_out/bench_small.json 2>gpurun_out/bench_small.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r01_step_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-hbm-kernels --profiler-range > gpurun_out/ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tc_igemm -c 2 -o gpurun_out/r01_top_kernel -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-hbm-kernels --profiler-range > gpurun_out/ncu2.log 2>&1
+tail -2 gpurun_out/ncu2.log | cut -c1-200

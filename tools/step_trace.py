@@ -18,6 +18,12 @@ from int8inferenceengine_b200 import backend as B, workloads as W  # noqa: E402
 from int8inferenceengine_b200.runner import build_module  # noqa: E402
 
 
+def short(name):
+    name = name.replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    base = name.split("(")[0]
+    return base[:80]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=100)
@@ -43,7 +49,7 @@ def main():
     for e in evs:
         d = e.time_range.end - e.time_range.start
         busy += d
-        a = agg.setdefault(e.name.split("(")[0][-70:], [0, 0.0])
+        a = agg.setdefault(short(e.name), [0, 0.0])
         a[0] += 1
         a[1] += d
     span = evs[-1].time_range.end - evs[0].time_range.start
@@ -59,7 +65,7 @@ def main():
     last = evs[-per:]
     t0 = last[0].time_range.start
     for e in last:
-        print(f"  {e.time_range.start - t0:8.1f} {e.time_range.end - e.time_range.start:7.2f}  {e.name.split('(')[0][-60:]}")
+        print(f"  {e.time_range.start - t0:8.1f} {e.time_range.end - e.time_range.start:7.2f}  {short(e.name)}")
 
 
 if __name__ == "__main__":
