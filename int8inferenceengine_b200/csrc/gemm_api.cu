@@ -57,6 +57,7 @@ struct i8ie_conv_plan {
   int c;     // real input channels
   // tcgen05 state
   int bk, bn;
+  int cluster;          // CTAs per cluster (weight tile multicast); tmB's box holds bn / cluster rows
   CUtensorMap tmB;
   int32_t* border_tab;  // device, owned
   MapCache amaps;
@@ -105,6 +106,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   p->stem_x = nullptr;
   p->stem_w = nullptr;
   p->c = c;
+  p->cluster = 1;
   const bool stem_ok = tc_stem_eligible(g, c) && !tc_disabled();
   const bool eligible = tc_conv_eligible(g) && !tc_disabled();
   if (impl == 2 && !eligible && !stem_ok) {
@@ -146,7 +148,8 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   if (rc == I8IE_OK && p->impl == 2) {
     p->bk = tc_conv_bk(g);
     p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
-    rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->bn);
+    p->cluster = tc_conv_cluster(p->bk, p->bn);
+    rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->cluster > 1 ? p->bn / 2 : p->bn);
     const int tab = tc_border_table_size(g);
     if (rc == I8IE_OK && tab > 0) {
       if (cudaMalloc(&p->border_tab, sizeof(int32_t) * (size_t)tab) != cudaSuccess) {
@@ -190,7 +193,7 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
       return tc_encode_act_map_im2col(m, x, plan->g, plan->bk);
     });
     if (rc != I8IE_OK) return rc;
-    return launch_tc_conv(plan->g, tmA, plan->tmB, plan->bk, plan->bn, plan->border_tab, y, ep, zp_in,
+    return launch_tc_conv(plan->g, tmA, plan->tmB, plan->bk, plan->bn, plan->cluster, plan->border_tab, y, ep, zp_in,
                           (cudaStream_t)stream);
   }
   return launch_simt_igemm(plan->g, x, plan->w_packed, y, ep, zp_in, (cudaStream_t)stream);

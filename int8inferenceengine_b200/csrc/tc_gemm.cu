@@ -51,6 +51,10 @@ struct TcParams {
   // 128-row sub-tiles per CTA tile (1 or 2): two accumulators share every weight stage, which
   // cuts the L2->SM bytes per MAC (the binding limit of a 128 x BN tile, ~43 B/clk/SM)
   int mt;
+  // thread-block cluster of `cluster` CTAs (1 or 2) along M: the CTAs of a cluster work on adjacent
+  // M tiles of the SAME N tile, each loads 1/cluster of the weight tile and TMA-multicasts it to all
+  // of them — the weight stream is the larger share of the L2->SM traffic this kernel is bound by
+  int cluster, tiles_mp;   // tiles_mp = ceil(tiles_m / cluster)
 };
 
 namespace {
@@ -191,15 +195,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mn_tiles = p.tiles_m * p.tiles_n;
+  const int cl = p.cluster;                               // cluster dims are (cl, 1, 1)
+  const int crank = cl > 1 ? (int)(blockIdx.x % cl) : 0;  // == %cluster_ctarank
+  const int mn_tiles = p.tiles_mp * p.tiles_n;            // tiles of a whole cluster (cl adjacent M tiles each)
   const int num_tiles = mn_tiles * p.splits;
+  const int tile0 = blockIdx.x / cl, tile_step = gridDim.x / cl;
+  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
-      ptx::mbar_init(&ctl->empty[s], 1);
+      ptx::mbar_init(&ctl->empty[s], cl);   // every CTA that reads the multicast weight tile releases it
     }
     for (int b = 0; b < (int)NACC; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
+  if (cl > 1) ptx::cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
@@ -219,9 +228,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     if (lane == 0) {
       uint32_t it = 0;
       bool alive = true;
-      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
         const int split = tile / mn_tiles, mn = tile % mn_tiles;
-        const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
+        // a cluster's tail tile beyond the last M tile re-loads the last one (its stores are masked)
+        const int mtile = min((mn / p.tiles_n) * cl + crank, p.tiles_m - 1);
+        const int m0 = mtile * BM * mt, n0 = (mn % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
         int bw[MT] = {}, bh[MT] = {}, bn[MT] = {};
         if (MODE == 1) {
@@ -253,7 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                 ptx::tma_load_2d(dst, &tmA, &ctl->full[s], kidx * BK, m0 + t * BM);
             }
             if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } } }
-            ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
+            if (cl > 1)   // my 1/cl of the weight rows, delivered to every CTA of the cluster
+              ptx::tma_load_2d_multicast(sb + j * kSubB + crank * (kSubB / cl), &tmB, &ctl->full[s], kidx * BK,
+                                         n0 + crank * (BN / cl), cmask);
+            else
+              ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
           }
         }
       }
@@ -265,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
       uint32_t it = 0, acc_it = 0;
       bool alive = true;
-      for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, acc_it += mt) {
+      for (int tile = tile0; tile < num_tiles && alive; tile += tile_step, acc_it += mt) {
         uint32_t d_tmem[MT];
 #pragma unroll
         for (int t = 0; t < mt; ++t) {
@@ -298,7 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             a_lo += (uint32_t)((mt * kSubA) >> 4);
             b_lo += (uint32_t)(kSubB >> 4);
           }
-          ptx::tc_commit(&ctl->empty[s]);   // slot reusable once these MMAs have read it
+          // slot reusable once these MMAs have read it; with a cluster every CTA's slot also holds
+          // weight rows multicast by the peers, so the release goes to all of them
+          if (cl > 1) ptx::tc_commit_multicast(&ctl->empty[s], cmask);
+          else ptx::tc_commit(&ctl->empty[s]);
         }
         if (alive) {
 #pragma unroll
@@ -315,10 +333,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     const float rcp = __frcp_rn(p.ep.sc);
     const bool has_bias = p.ep.bias_f != nullptr;
     uint32_t tcount = 0, acc_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount, acc_it += mt) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount, acc_it += mt) {
       const uint32_t ob = tcount & 1;
       const int split = tile / mn_tiles, mn = tile % mn_tiles;
-      const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
+      const int mtile = (mn / p.tiles_n) * cl + crank;
+      const bool tile_valid = mtile < p.tiles_m;          // false: a cluster's tail tile past the last M tile
+      const int m0 = min(mtile, p.tiles_m - 1) * BM * mt, n0 = (mn % p.tiles_n) * BN;
       if (p.splits <= 1) {
         // stage this tile's per-channel offsets (double-buffered: one barrier per tile)
         for (int j = et; j < BN; j += 32 * kEpiWarps) {
@@ -344,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
-            if (m < p.M && ok) {
+            if (m < p.M && ok && tile_valid) {
 #pragma unroll
               for (int g = 0; g < 8; ++g)
                 *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -365,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
           const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
           if (!ok) atomicCAS(&g_tc_error, 0, 3);
           ptx::tc_fence_after();
-          epilogue_row<BN>(p, t_row, (m < p.M && ok) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
+          epilogue_row<BN>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
                            ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
         }
         // hand the accumulator buffer back to the MMA warp
@@ -377,7 +397,164 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (cl > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer may still multicast to it or arrive on its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
+}
+
+// ---- CTA-pair kernel (cta_group::2): conv with wide N tiles ------------------------------------
+// A 128 x BN tile per SM needs (128 + BN) * BK bytes per K block through the SM's L2 port, which is
+// what bounds tc_igemm_kernel (ncu: ~46 B/clk/SM, tensor pipe ~50 % busy). Here two SMs of a
+// cluster work on ONE 256 x BN tile: each CTA loads its own 128 rows of A and only HALF of the
+// weight rows; tcgen05.mma.cta_group::2 (issued by the even CTA) reads both halves and fills both
+// CTAs' TMEM (rows 0-127 / 128-255). Per-SM operand traffic drops to (128 + BN/2) * BK.
+//   full[s]       even CTA only, 1 arrival (its producer, expecting the bytes of BOTH CTAs)
+//   empty[s]      each CTA, 1 arrival (the even CTA's multicast commit)
+//   tmem_full[b]  each CTA, 1 arrival (multicast commit)
+//   tmem_empty[b] even CTA only, 2 * kEpiWarps arrivals (the epilogue warps of both CTAs)
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int BK = 128;
+  constexpr int kSubA = BM * BK, kSubBh = (BN / 2) * BK;
+  constexpr int kStage = kSubA + kSubBh;
+  constexpr uint32_t NACC = num_acc<BN>();
+  TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)(blockIdx.x & 1);     // cluster dims (2, 1, 1)
+  const bool leader = crank == 0;
+  const int mn_tiles = p.tiles_mp * p.tiles_n;
+  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < (int)NACC; ++b) {
+      ptx::mbar_init(&ctl->tmem_full[b], 1);
+      ptx::mbar_init(&ctl->tmem_empty[b], 2 * kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_2cta(&ctl->tmem_slot, tmem_cols<BN>());
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_slot;
+  ptx::cluster_sync_all();   // the peer's barriers and TMEM exist before anything targets them
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of A, own half of the weight rows =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      bool alive = true;
+      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step) {
+        const int mtile = min((tile / p.tiles_n) * 2 + crank, p.tiles_m - 1);   // tail: re-load the last tile, stores masked
+        const int m0 = mtile * BM, n0 = (tile % p.tiles_n) * BN;
+        const int q = m0 % p.ow, r = m0 / p.ow;
+        const int bw = q * p.stride_w - p.pad, bh = (r % p.oh) * p.stride_h - p.pad, bimg = r / p.oh;
+        int cb = 0, kx = 0, ky = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+          if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], 2u * (uint32_t)kStage);
+          uint8_t* sa = smem + (size_t)s * kStage;
+          ptx::tma_load_im2col_4d_2cta(sa, &tmA, &ctl->full[s], cb * BK, bw, bh, bimg, (uint16_t)kx, (uint16_t)ky);
+          if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
+          ptx::tma_load_2d_2cta(sa + kSubA, &tmB, &ctl->full[s], kb * BK, n0 + crank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the even CTA drives the tensor cores of both SMs =====
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_i8(2 * BM, BN);
+      const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
+      uint32_t it = 0, acc_it = 0;
+      bool alive = true;
+      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step, ++acc_it) {
+        const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
+        if (!ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * acc_stride<BN>();
+        uint32_t accf = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
+          const uint32_t a_lo = ptx::smem_desc_lo(sa), b_lo = ptx::smem_desc_lo(sa + kSubA);
+#pragma unroll
+          for (int k = 0; k < BK / 32; ++k) {
+            ptx::mma_i8_ss_lohi_2cta(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), desc_hi, b_lo + (uint32_t)((k * 32) >> 4),
+                                     desc_hi, idesc, accf);
+            accf = 1;
+          }
+          ptx::tc_commit_2cta_multicast(&ctl->empty[s], 3);   // both CTAs' slots are free once these MMAs have read them
+        }
+        if (alive) ptx::tc_commit_2cta_multicast(&ctl->tmem_full[slot], 3);
+      }
+      if (!alive)   // unblock both epilogues so that the CTAs can exit
+        for (int b = 0; b < (int)NACC; ++b) { ptx::mbar_arrive(&ctl->tmem_full[b]); ptx::mbar_arrive_remote(&ctl->tmem_full[b], 1); }
+    }
+  } else {
+    // ===== epilogue (both CTAs): this CTA's 128 rows of the 256-row tile =====
+    const int quad = warp & 3;
+    const int et = threadIdx.x - 64;
+    const float rcp = __frcp_rn(p.ep.sc);
+    uint32_t tcount = 0, acc_it = 0;
+    for (int tile = tile0; tile < mn_tiles; tile += tile_step, ++tcount, ++acc_it) {
+      const uint32_t ob = tcount & 1;
+      const int mtile = (tile / p.tiles_n) * 2 + crank;
+      const bool tile_valid = mtile < p.tiles_m;
+      const int m0 = min(mtile, p.tiles_m - 1) * BM, n0 = (tile % p.tiles_n) * BN;
+      for (int j = et; j < BN; j += 32 * kEpiWarps) {
+        const int n = n0 + j;
+        ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
+        ctl->bias[ob][j] = 0.f;
+      }
+      epi_bar_sync();
+      const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
+      const int m = m0 + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + slot * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
+      const int32_t* corr = nullptr;
+      if (p.border_tab && m < p.M) {
+        const int q = m % p.ow, pr = (m / p.ow) % p.oh;
+        const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
+        const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
+        const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
+        const int d = p.pad + 1;
+        const int cls = ((th * d + bh) * d + tw) * d + bw;
+        if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
+      }
+      const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
+      if (!ok) atomicCAS(&g_tc_error, 0, 3);
+      ptx::tc_fence_after();
+      epilogue_row<BN>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
+                       ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
+      // hand the accumulator buffer (both halves) back to the even CTA's MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&ctl->tmem_empty[slot]);
+        else ptx::mbar_arrive_remote(&ctl->tmem_empty[slot], 0);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // no CTA leaves while its peer may still use its shared memory, barriers or TMEM
+  if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols<BN>());
 }
 
 // ---- stem2: smem-resident stem rows, sliding windows expressed by overlapping descriptors ---
@@ -856,9 +1033,10 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
     I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  const int tiles = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
+  const int tiles = p.tiles_mp * p.tiles_n * p.splits;          // cluster tiles
+  const int max_clusters = num_sms() / p.cluster;
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * p.cluster;
+  launch_cluster_pdl(p.cluster, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
 
@@ -888,6 +1066,10 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaS
   const int smem = stages * kStage + ctl_bytes + 1024;
   p.tiles_m = (p.M + BM * p.mt - 1) / (BM * p.mt);
   p.tiles_n = (p.out_cp + BN - 1) / BN;
+  const int want_cluster = p.cluster < 1 ? 1 : p.cluster;
+  if (p.cluster < 1 || p.mt != 1 || p.splits > 1) p.cluster = 1;
+  I8IE_REQUIRE(p.cluster == want_cluster, "tcgen05: a %d-CTA cluster needs single 128-row tiles without split-K", want_cluster);
+  p.tiles_mp = (p.tiles_m + p.cluster - 1) / p.cluster;
   if (p.splits < 1) { p.splits = 1; p.kb_per = p.num_kb; }
   if constexpr (kHasMT2) {
     if (p.mt == 2) return launch_kernel<BN, BK, MODE, 2>(tmA, tmB, p, smem, stream);
@@ -918,6 +1100,34 @@ int launch_bk(int bk, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, co
   }
   set_error("tcgen05: unsupported BK %d", bk);
   return I8IE_EINVAL;
+}
+
+// CTA-pair launch (see tc_igemm2_kernel): BK = 128, one K block per stage, 128-row tiles
+template <int BN>
+int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
+  constexpr int kMaxSmem = 227 * 1024;
+  const int ctl_bytes = (int)sizeof(TcControl<BN>);
+  const int kStage = BM * 128 + (BN / 2) * 128;
+  int stages = (kMaxSmem - 1024 - ctl_bytes) / kStage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  I8IE_REQUIRE(stages >= 2, "tcgen05 pair: no room for a pipeline");
+  p.stages = stages;
+  const int smem = stages * kStage + ctl_bytes + 1024;
+  p.mt = 1; p.splits = 1; p.kb_per = p.num_kb; p.cluster = 2;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.out_cp + BN - 1) / BN;
+  p.tiles_mp = (p.tiles_m + 1) / 2;
+  static int attr_smem = 0;
+  auto kern = tc_igemm2_kernel<BN>;
+  if (attr_smem < smem) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int tiles = p.tiles_mp * p.tiles_n;
+  const int max_clusters = num_sms() / 2;
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
+  launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
+  return check_launch("tc_igemm2_kernel");
 }
 
 // sub-blocks per pipeline stage: short K blocks are batched so that one mbarrier round trip
@@ -988,7 +1198,19 @@ int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int 
 
 int tc_pick_bn(int n) { return pick_bn(n); }
 
-int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn,
+// Cluster mode of a conv plan: 1 = single CTAs; 2 = CTA pairs, tcgen05.mma.cta_group::2 with the
+// weight tile split across the pair (default for wide tiles); 3 = 2-CTA clusters of independent
+// 128-row tiles with the weight tile TMA-multicast (opt-in I8IE_CLUSTER_MC=1: measured slower, the
+// bound is the per-SM ingest, which multicast does not reduce). For 2 and 3 the weight tensor map's
+// box holds bn / 2 rows (whole 1 KB swizzle atoms).
+int tc_conv_cluster(int bk, int bn) {
+  if (std::getenv("I8IE_NO_CLUSTER") != nullptr) return 1;
+  const bool ok = bk == 128 && (bn == 256 || bn == 192 || bn == 128) && ((bn / 2) * bk) % 1024 == 0;
+  if (!ok) return 1;
+  return std::getenv("I8IE_CLUSTER_MC") != nullptr ? 3 : 2;
+}
+
+int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream) {
   TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
@@ -998,7 +1220,18 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
-  p.mt = 2;   // launch_cfg falls back to 1 when the shape is too small for it
+  if (cluster == 2) {   // CTA pairs
+    I8IE_REQUIRE(bk == 128, "tcgen05 pair: needs 128-byte K blocks");
+    switch (bn) {
+      case 128: return launch_pair_bn<128>(tmA, tmB, p, stream);
+      case 192: return launch_pair_bn<192>(tmA, tmB, p, stream);
+      case 256: return launch_pair_bn<256>(tmA, tmB, p, stream);
+    }
+    set_error("tcgen05 pair: unsupported BN %d", bn);
+    return I8IE_EINVAL;
+  }
+  p.cluster = cluster == 3 ? 2 : 1;
+  p.mt = p.cluster > 1 ? 1 : 2;   // launch_cfg falls back to 1 when the shape is too small for it
   return launch_bk<1>(bk, bn, tmA, tmB, p, stream);
 }
 
