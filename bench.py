@@ -283,6 +283,7 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     sampler.active = False
     ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0 + model.graph_launches() - glaunch0   # timed steps only
     clock_window = "timed region"
     if len(sampler.samples) < 5 and not args.profiler_range:
         # the timed region is only a few milliseconds (NVML answers in ~ms): keep sampling over
@@ -294,7 +295,6 @@ def run_ours(args):
         sync_all()
         sampler.active = False
         clock_window = f"timed region + {extra} further identical steps (untimed, ~0.5 s)"
-    launches = _lib.launch_count() - launches0 + model.graph_launches() - glaunch0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
