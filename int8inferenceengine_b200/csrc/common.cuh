@@ -270,6 +270,18 @@ __device__ __forceinline__ float4 ld_stream_f4(const void* p) {
                : "l"(p));
   return r;
 }
+// read-once input that should not displace the L2-resident working set (weights, activations)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float2 ld_evict_first_f2(const void* p, uint64_t pol) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+               : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
   uint32_t r;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));

@@ -149,6 +149,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
     p->bk = tc_conv_bk(g);
     p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
     p->cluster = tc_conv_cluster(p->bk, p->bn);
+    if (p->cluster == 2 && tc_conv_strip_eligible(g, p->bk, p->bn)) p->cluster = 4;   // pair kernel with A strips
     rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->cluster > 1 ? p->bn / 2 : p->bn);
     const int tab = tc_border_table_size(g);
     if (rc == I8IE_OK && tab > 0) {
@@ -189,8 +190,8 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   }
   if (plan->impl == 2) {
     CUtensorMap tmA;
-    int rc = plan->amaps.get(x, 0, 0, 0, 0, &tmA, [&](CUtensorMap* m) {
-      return tc_encode_act_map_im2col(m, x, plan->g, plan->bk);
+    int rc = plan->amaps.get(x, plan->cluster == 4, 0, 0, 0, &tmA, [&](CUtensorMap* m) {
+      return plan->cluster == 4 ? tc_encode_act_map_strip(m, x, plan->g) : tc_encode_act_map_im2col(m, x, plan->g, plan->bk);
     });
     if (rc != I8IE_OK) return rc;
     return launch_tc_conv(plan->g, tmA, plan->tmB, plan->bk, plan->bn, plan->cluster, plan->border_tab, y, ep, zp_in,

@@ -36,6 +36,8 @@ int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* ta
 int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn);
 int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int bk);
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx);
+bool tc_conv_strip_eligible(const GemmGeom& g, int bk, int bn);   // stride-1 A-strip variant of the pair kernel
+int tc_encode_act_map_strip(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g);
 int tc_conv_cluster(int bk, int bn);   // CTAs per cluster sharing one multicast weight tile (1 or 2)
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream);

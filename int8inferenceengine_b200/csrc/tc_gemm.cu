@@ -55,6 +55,10 @@ struct TcParams {
   // M tiles of the SAME N tile, each loads 1/cluster of the weight tile and TMA-multicasts it to all
   // of them — the weight stream is the larger share of the L2->SM traffic this kernel is bound by
   int cluster, tiles_mp;   // tiles_mp = ceil(tiles_m / cluster)
+  // strip kernel (tc_igemm2s_kernel): output positions are enumerated over the PADDED width
+  // owp = W + 2*pad (the last kw-1 positions of a row are computed but never stored), Mp = n*oh*owp
+  int owp, Mp, stages_a;
+  int strip_bo;   // probe: 1 = set the descriptor base-offset field for row-shifted strip starts
 };
 
 namespace {
@@ -557,6 +561,201 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
   if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols<BN>());
 }
 
+// ---- CTA-pair kernel with A strips (stride-1 convs) -----------------------------------------------
+// im2col fetches every input pixel once per filter tap. For stride 1 the kw taps of one filter row
+// read the SAME pixels shifted by one: if output positions are enumerated over the padded width
+// (owp = W + 2*pad positions per row, the last kw-1 are garbage and never stored), tap kx of output
+// position m is row m + kx of ONE strip of 128 + kw - 1 consecutive positions at tap 0. So the
+// producer loads one strip per (filter row, channel block) and the MMA walks the kw taps by moving
+// the A descriptor's start address one 128-byte row at a time (descriptor base-offset field = the
+// row's position inside the 8-row swizzle atom). A ingest per K block falls from 16 KB to
+// 16.5 KB / kw; with the weight half (BN/2 x 128 B) the pair is no longer bound by the L2 port.
+// Two rings: weight K blocks (full/empty, as before) and A strips (a_full/a_empty).
+constexpr int kStripRows = 136;                 // 128 + (kw - 1) <= 136 -> kw <= 9
+constexpr int kStripBytes = kStripRows * 128;   // 17 x 1 KB swizzle atoms
+constexpr int kMaxStagesA = 4;
+
+template <int BN>
+struct alignas(16) TcControlS {
+  TcControl<BN> c;
+  uint64_t a_full[kMaxStagesA];
+  uint64_t a_empty[kMaxStagesA];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc_igemm2s_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int BK = 128;
+  constexpr int kSubBh = (BN / 2) * BK;
+  constexpr uint32_t NACC = num_acc<BN>();
+  uint8_t* sB = smem;                                            // [stages][BN/2 x 128]
+  uint8_t* sS = smem + (size_t)p.stages * kSubBh;                // [stages_a][136 x 128]
+  TcControlS<BN>* cs = reinterpret_cast<TcControlS<BN>*>(sS + (size_t)p.stages_a * kStripBytes);
+  TcControl<BN>* ctl = &cs->c;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)(blockIdx.x & 1);
+  const bool leader = crank == 0;
+  const int mn_tiles = p.tiles_mp * p.tiles_n;
+  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+  const uint32_t strip_bytes = (uint32_t)(BM + p.kw - 1) * BK;   // bytes one strip load delivers
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < p.stages_a; ++s) {
+      ptx::mbar_init(&cs->a_full[s], 1);
+      ptx::mbar_init(&cs->a_empty[s], 1);
+    }
+    for (int b = 0; b < (int)NACC; ++b) {
+      ptx::mbar_init(&ctl->tmem_full[b], 1);
+      ptx::mbar_init(&ctl->tmem_empty[b], 2 * kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_2cta(&ctl->tmem_slot, tmem_cols<BN>());
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_slot;
+  ptx::cluster_sync_all();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== producer (both CTAs): one A strip per (filter row, channel block), kw weight blocks =====
+    if (lane == 0) {
+      uint32_t itb = 0, ita = 0;
+      bool alive = true;
+      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step) {
+        const int mtile = min((tile / p.tiles_n) * 2 + crank, p.tiles_m - 1);
+        const int m0 = mtile * BM, n0 = (tile % p.tiles_n) * BN;
+        const int q = m0 % p.owp, r = m0 / p.owp;
+        const int bw = q - p.pad, bh = (r % p.oh) - p.pad, bimg = r / p.oh;
+        for (int ky = 0; ky < p.kh && alive; ++ky) {
+          for (int cb = 0; cb < p.cblocks && alive; ++cb, ++ita) {
+            const int sa = ita % p.stages_a;
+            const uint32_t pha = (ita / p.stages_a) & 1;
+            if (!ptx::mbar_wait(&cs->a_empty[sa], pha ^ 1)) { atomicCAS(&g_tc_error, 0, 6); alive = false; break; }
+            if (leader) ptx::mbar_arrive_expect_tx(&cs->a_full[sa], 2u * strip_bytes);
+            ptx::tma_load_im2col_4d_2cta(sS + (size_t)sa * kStripBytes, &tmA, &cs->a_full[sa], cb * BK, bw, bh, bimg, 0,
+                                         (uint16_t)ky);
+            for (int kx = 0; kx < p.kw; ++kx, ++itb) {
+              const int s = itb % p.stages;
+              const uint32_t ph = (itb / p.stages) & 1;
+              if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+              if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], 2u * (uint32_t)kSubBh);
+              ptx::tma_load_2d_2cta(sB + (size_t)s * kSubBh, &tmB, &ctl->full[s],
+                                    ((ky * p.kw + kx) * p.cblocks + cb) * BK, n0 + crank * (BN / 2));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (even CTA): tap kx = the strip read kx rows further down =====
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_i8(2 * BM, BN);
+      const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
+      uint32_t itb = 0, ita = 0, acc_it = 0;
+      bool alive = true;
+      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step, ++acc_it) {
+        const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
+        if (!ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + slot * acc_stride<BN>();
+        uint32_t accf = 0;
+        for (int ky = 0; ky < p.kh && alive; ++ky) {
+          for (int cb = 0; cb < p.cblocks && alive; ++cb, ++ita) {
+            const int sa = ita % p.stages_a;
+            const uint32_t pha = (ita / p.stages_a) & 1;
+            if (!ptx::mbar_wait(&cs->a_full[sa], pha)) { atomicCAS(&g_tc_error, 0, 7); alive = false; break; }
+            ptx::tc_fence_after();
+            const uint32_t strip = ptx::smem_u32(sS + (size_t)sa * kStripBytes);   // 1 KB aligned
+            for (int kx = 0; kx < p.kw; ++kx, ++itb) {
+              const int s = itb % p.stages;
+              const uint32_t ph = (itb / p.stages) & 1;
+              if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+              ptx::tc_fence_after();
+              // start address kx rows into the strip; base offset = row position inside the swizzle atom
+              const uint32_t a_lo = ptx::smem_desc_lo(strip + (uint32_t)((p.strip_bo & 2) ? 0 : kx) * BK);
+              const uint32_t a_hi = desc_hi | (p.strip_bo ? ((uint32_t)(kx & 7) << 17) : 0u);
+              const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(sB + (size_t)s * kSubBh));
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) {
+                ptx::mma_i8_ss_lohi_2cta(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), a_hi, b_lo + (uint32_t)((k * 32) >> 4),
+                                         desc_hi, idesc, accf);
+                accf = 1;
+              }
+              ptx::tc_commit_2cta_multicast(&ctl->empty[s], 3);
+            }
+            if (alive) ptx::tc_commit_2cta_multicast(&cs->a_empty[sa], 3);   // strip free in both CTAs
+          }
+        }
+        if (alive) ptx::tc_commit_2cta_multicast(&ctl->tmem_full[slot], 3);
+      }
+      if (!alive)
+        for (int b = 0; b < (int)NACC; ++b) { ptx::mbar_arrive(&ctl->tmem_full[b]); ptx::mbar_arrive_remote(&ctl->tmem_full[b], 1); }
+    }
+  } else {
+    // ===== epilogue (both CTAs): rows are positions of the padded enumeration =====
+    const int quad = warp & 3;
+    const int et = threadIdx.x - 64;
+    const float rcp = __frcp_rn(p.ep.sc);
+    uint32_t tcount = 0, acc_it = 0;
+    for (int tile = tile0; tile < mn_tiles; tile += tile_step, ++tcount, ++acc_it) {
+      const uint32_t ob = tcount & 1;
+      const int mtile = (tile / p.tiles_n) * 2 + crank;
+      const bool tile_valid = mtile < p.tiles_m;
+      const int m0 = min(mtile, p.tiles_m - 1) * BM, n0 = (tile % p.tiles_n) * BN;
+      for (int j = et; j < BN; j += 32 * kEpiWarps) {
+        const int n = n0 + j;
+        ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
+        ctl->bias[ob][j] = 0.f;
+      }
+      epi_bar_sync();
+      const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
+      const int mp = m0 + quad * 32 + lane;               // position in the padded enumeration
+      const int q = mp % p.owp, rr = mp / p.owp;
+      const int pr = rr % p.oh, img = rr / p.oh;
+      const bool row_valid = tile_valid && mp < p.Mp && q < p.ow;
+      const long long m = ((long long)img * p.oh + pr) * p.ow + q;   // reference row index (conv2d.cc:39-42)
+      const uint32_t t_row = tmem_base + slot * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
+      const int32_t* corr = nullptr;
+      if (p.border_tab && row_valid) {
+        const int y0 = pr - p.pad, x0 = q - p.pad;
+        const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
+        const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
+        const int d = p.pad + 1;
+        const int cls = ((th * d + bh) * d + tw) * d + bw;
+        if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
+      }
+      const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
+      if (!ok) atomicCAS(&g_tc_error, 0, 3);
+      ptx::tc_fence_after();
+      epilogue_row<BN>(p, t_row, (row_valid && ok) ? m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
+                       ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&ctl->tmem_empty[slot]);
+        else ptx::mbar_arrive_remote(&ctl->tmem_empty[slot], 0);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols<BN>());
+}
+
 // ---- stem2: smem-resident stem rows, sliding windows expressed by overlapping descriptors ---
 // For stride-4 stems the window of output pixel q starts at superpixel q, i.e. 16 bytes after
 // the window of q-1: exactly the fixed row pitch of a NO-SWIZZLE K-major UMMA core matrix
@@ -818,6 +1017,7 @@ __global__ void __launch_bounds__(256) stem_quantize_kernel(const float* __restr
   const int row = y - pad;
   const uint32_t zp4 = zp * 0x01010101u;
   uint32_t wd[4] = {zp4, zp4, zp4, zp4};
+  const uint64_t pol = l2_evict_first_policy();   // the fp32 image is read once: keep weights/activations in L2
   if (row >= 0 && row < h) {
     const int64_t plane = (int64_t)h * w;
     const int col0 = sx * 4 - pad;
@@ -1130,6 +1330,36 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, c
   return check_launch("tc_igemm2_kernel");
 }
 
+// strip variant of the CTA-pair launch (see tc_igemm2s_kernel)
+template <int BN>
+int launch_pair_strip_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
+  constexpr int kMaxSmem = 227 * 1024;
+  const int ctl_bytes = (int)sizeof(TcControlS<BN>);
+  const int kSubBh = (BN / 2) * 128;
+  p.stages_a = 3;
+  p.strip_bo = std::getenv("I8IE_STRIP_BO") != nullptr ? std::atoi(std::getenv("I8IE_STRIP_BO")) : 0;
+  int stages = (kMaxSmem - 1024 - ctl_bytes - p.stages_a * kStripBytes) / kSubBh;
+  if (stages > kMaxStages) stages = kMaxStages;
+  I8IE_REQUIRE(stages >= 3, "tcgen05 strip pair: no room for a pipeline");
+  p.stages = stages;
+  const int smem = stages * kSubBh + p.stages_a * kStripBytes + ctl_bytes + 1024;
+  p.mt = 1; p.splits = 1; p.kb_per = p.num_kb; p.cluster = 2;
+  p.tiles_m = (p.Mp + BM - 1) / BM;
+  p.tiles_n = (p.out_cp + BN - 1) / BN;
+  p.tiles_mp = (p.tiles_m + 1) / 2;
+  static int attr_smem = 0;
+  auto kern = tc_igemm2s_kernel<BN>;
+  if (attr_smem < smem) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  const int tiles = p.tiles_mp * p.tiles_n;
+  const int max_clusters = num_sms() / 2;
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
+  launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
+  return check_launch("tc_igemm2s_kernel");
+}
+
 // sub-blocks per pipeline stage: short K blocks are batched so that one mbarrier round trip
 // covers >= 96..128 bytes of K (must divide the per-tap block count)
 int pick_ksub(int bk, int cblocks) {
@@ -1192,6 +1422,34 @@ int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& 
   return encode_im2col_4d(tm, x, g, bk);
 }
 
+// A-strip view (tc_igemm2s_kernel): tap (0, ky) only, output positions enumerated over the padded
+// width (upper corner +pad, as if kw were 1), 128 + kw - 1 positions per load.
+int tc_encode_act_map_strip(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g) {
+  static EncodeIm2colFn fn = driver_fn<EncodeIm2colFn>("cuTensorMapEncodeIm2col");
+  I8IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)g.cp, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
+  cuuint64_t strides[3] = {(cuuint64_t)g.cp, (cuuint64_t)g.cp * g.w, (cuuint64_t)g.cp * g.w * g.h};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad, g.pad - (g.kh - 1)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x), dims, strides, lower, upper, 128,
+                  (cuuint32_t)(BM + g.kw - 1), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  I8IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col (strip view) failed (%d): c=%d w=%d h=%d n=%d k=%dx%d p=%d",
+               (int)r, g.cp, g.w, g.h, g.n, g.kh, g.kw, g.pad);
+  return I8IE_OK;
+}
+
+bool tc_conv_strip_eligible(const GemmGeom& g, int bk, int bn) {
+  // measured on B200: bit-exact but slower than the plain pair kernel (545 vs 402 us for conv2 at
+  // batch 1000; the padded enumeration adds 15 % tiles and the operand ingest it saves is not what
+  // bounds the pair kernel) -> opt-in only
+  if (std::getenv("I8IE_STRIP") == nullptr) return false;
+  const long long mp = (long long)g.n * g.oh * (g.w + 2 * g.pad);
+  return tc_conv_cluster(bk, bn) == 2 && g.stride == 1 && g.kw >= 2 && g.kw <= kStripRows - BM + 1 && g.cp % 128 == 0 &&
+         mp < (1ll << 31) - 256;
+}
+
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx) {
   return encode_tiled_2d(tm, x, (uint64_t)k, (uint64_t)m, (uint64_t)ldx, 128, BM);
 }
@@ -1220,6 +1478,17 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  if (cluster == 4) {   // CTA pairs with A strips (stride 1)
+    p.owp = g.w + 2 * g.pad;
+    p.Mp = g.n * g.oh * p.owp;
+    switch (bn) {
+      case 128: return launch_pair_strip_bn<128>(tmA, tmB, p, stream);
+      case 192: return launch_pair_strip_bn<192>(tmA, tmB, p, stream);
+      case 256: return launch_pair_strip_bn<256>(tmA, tmB, p, stream);
+    }
+    set_error("tcgen05 strip pair: unsupported BN %d", bn);
+    return I8IE_EINVAL;
+  }
   if (cluster == 2) {   // CTA pairs
     I8IE_REQUIRE(bk == 128, "tcgen05 pair: needs 128-byte K blocks");
     switch (bn) {
