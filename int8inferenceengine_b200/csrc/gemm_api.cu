@@ -185,7 +185,7 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
     int rc = tc_stem_pack_input(plan->g, plan->stem, x, plan->stem_x, zp_in, (cudaStream_t)stream);
     if (rc != I8IE_OK) return rc;
     if (plan->stem2)
-      return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+      return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
     return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
   }
   if (plan->impl == 2) {
@@ -207,11 +207,16 @@ static int conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, const float*
   I8IE_REQUIRE(plan->impl == 3, "conv2d_f32_u8: only stem plans fuse the input quantise (plan impl=%d)", plan->impl);
   I8IE_REQUIRE(in_zp >= 0 && in_zp <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_f32_u8: zero point out of range");
   EpiParams ep{oc, nullptr, in_scale, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  if (plan->stem2 && tc_stem2_can_fuse_quantize(plan->g, plan->c, x_nchw, x_slot, in_scale)) {
+    // the stem kernel's producer warps quantise the fp32 image straight into its operand ring
+    const StemF32Src src{x_nchw, x_slot, in_scale, in_zp};
+    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, &src, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+  }
   int rc = tc_stem_quantize_input(plan->g, plan->stem, x_nchw, x_slot, plan->stem_x, in_scale, in_zp,
                                   (cudaStream_t)stream);
   if (rc != I8IE_OK) return rc;
   if (plan->stem2)
-    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
   return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
 }
 

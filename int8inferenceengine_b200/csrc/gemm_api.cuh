@@ -61,8 +61,17 @@ int tc_stem_quantize_input(const GemmGeom& g, const StemGeom& s, const float* x,
                            cudaStream_t stream);
 int tc_encode_stem_act_map(CUtensorMap* tm, const uint8_t* xs, const GemmGeom& g, const StemGeom& s);
 bool tc_stem2_eligible(const GemmGeom& g, int c);
-int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const CUtensorMap& tmB, int bn,
-                    uint8_t* y, const EpiParams& ep, cudaStream_t stream);
+// fp32 NCHW source of a fused input quantise (direct pointer or run-time address slot)
+struct StemF32Src {
+  const float* x;
+  const float* const* xslot;
+  float scale;
+  int zp;
+};
+bool tc_stem2_can_fuse_quantize(const GemmGeom& g, int c, const float* x, const float* const* xslot, float scale);   // RGB stems
+// f32 == nullptr: rows come from the bordered u8 stem image xs; otherwise the kernel quantises them itself
+int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const StemF32Src* f32,
+                    const CUtensorMap& tmB, int bn, uint8_t* y, const EpiParams& ep, cudaStream_t stream);
 int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
                    const EpiParams& ep, cudaStream_t stream);
 

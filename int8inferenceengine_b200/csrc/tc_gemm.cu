@@ -31,6 +31,19 @@ namespace i8ie {
 
 __device__ int g_tc_error = 0;  // first protocol error seen by any tensor-core kernel (0 = none)
 
+constexpr uint32_t kDefaultWaitHintNs = 0;
+// dev knob: I8IE_WAIT_HINT=<ns> sets the mbarrier suspend-time hint of every tensor-core kernel
+// (set once, when the first tensor map of the process is encoded: never inside a graph capture)
+static void tc_apply_wait_hint() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  uint32_t v = kDefaultWaitHintNs;
+  if (const char* e = std::getenv("I8IE_WAIT_HINT")) v = (uint32_t)std::atoi(e);
+  cudaMemcpyToSymbol(ptx::g_wait_hint_ns, &v, sizeof(v));
+}
+
+
 struct TcParams {
   int M, N, out_cp;
   int tiles_m, tiles_n;
@@ -58,7 +71,6 @@ struct TcParams {
   // strip kernel (tc_igemm2s_kernel): output positions are enumerated over the PADDED width
   // owp = W + 2*pad (the last kw-1 positions of a row are computed but never stored), Mp = n*oh*owp
   int owp, Mp, stages_a;
-  int strip_bo;   // probe: 1 = set the descriptor base-offset field for row-shifted strip starts
 };
 
 namespace {
@@ -69,7 +81,14 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, then 
 // stem kernel: its K is tiny (22 MMAs per tile), so the fp32 epilogue is the longest stage; with two
 // warps per sub-partition it runs latency-bound, four warps per sub-partition hide the dependent chains
 constexpr int kStemEpiWarps = 16;
-constexpr int kStemThreads = 64 + 32 * kStemEpiWarps;
+// fused-quantise variant: 8 producer warps (2 rows of a 15/16-row tile each) next to the epilogue
+// warps — one epilogue warp per (quadrant, 32-column chunk) for the 96-channel tile, else 2 per quadrant
+constexpr int kStemProdWarps = 8;
+constexpr int kStemFBar = 8;   // first barrier slot of the fp32 row ring (operand ring has <= 6 stages)
+template <int BN, bool FQ>
+constexpr int stem_epi_warps() { return !FQ ? kStemEpiWarps : (BN == 96 ? 12 : 8); }
+template <int BN, bool FQ>
+constexpr int stem_threads() { return 64 + 32 * (stem_epi_warps<BN, FQ>() + (FQ ? kStemProdWarps : 0)); }
 constexpr int kMaxStages = 16;
 
 template <int BN>
@@ -567,10 +586,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
 // (owp = W + 2*pad positions per row, the last kw-1 are garbage and never stored), tap kx of output
 // position m is row m + kx of ONE strip of 128 + kw - 1 consecutive positions at tap 0. So the
 // producer loads one strip per (filter row, channel block) and the MMA walks the kw taps by moving
-// the A descriptor's start address one 128-byte row at a time (descriptor base-offset field = the
-// row's position inside the 8-row swizzle atom). A ingest per K block falls from 16 KB to
-// 16.5 KB / kw; with the weight half (BN/2 x 128 B) the pair is no longer bound by the L2 port.
-// Two rings: weight K blocks (full/empty, as before) and A strips (a_full/a_empty).
+// the A descriptor's start address one 128-byte row at a time. A ingest per K block falls from
+// 16 KB to 16.5 KB / kw. Two rings: weight K blocks (full/empty, as before) and A strips
+// (a_full/a_empty). Bit-exact, but measured SLOWER than the plain pair kernel (the 15 % extra
+// positions cost more than the saved ingest buys), so it is opt-in (I8IE_STRIP=1) — kept as the
+// starting point for physically padded activations, where the extra positions disappear.
 constexpr int kStripRows = 136;                 // 128 + (kw - 1) <= 136 -> kw <= 9
 constexpr int kStripBytes = kStripRows * 128;   // 17 x 1 KB swizzle atoms
 constexpr int kMaxStagesA = 4;
@@ -684,9 +704,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2s_kernel(const __grid_co
               const uint32_t ph = (itb / p.stages) & 1;
               if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
               ptx::tc_fence_after();
-              // start address kx rows into the strip; base offset = row position inside the swizzle atom
-              const uint32_t a_lo = ptx::smem_desc_lo(strip + (uint32_t)((p.strip_bo & 2) ? 0 : kx) * BK);
-              const uint32_t a_hi = desc_hi | (p.strip_bo ? ((uint32_t)(kx & 7) << 17) : 0u);
+              // start address kx rows into the strip. The 128-byte swizzle is a function of the absolute
+              // shared-memory address, so a row-shifted start needs NO descriptor base offset (measured:
+              // setting the base-offset field to the row position gives wrong accumulators)
+              const uint32_t a_lo = ptx::smem_desc_lo(strip + (uint32_t)kx * BK);
+              const uint32_t a_hi = desc_hi;
               const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(sB + (size_t)s * kSubBh));
 #pragma unroll
               for (int k = 0; k < BK / 32; ++k) {
@@ -756,6 +778,128 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2s_kernel(const __grid_co
   if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols<BN>());
 }
 
+// One superpixel (4 px x 4 channel lanes = 16 bytes) of the bordered stem image, quantised straight
+// from the fp32 NCHW input (quantize_utils.cc:44-52): row y / superpixel sx of the bordered image.
+// Split into a load half (all global loads of a superpixel issued back to back, so that a caller
+// can put several superpixels in flight) and a quantise half.
+// VEC2: pad and w even -> the 4 pixels are two aligned float2 per channel plane.
+// FAST: packed fp32x2 quantise behind one magnitude test (quant2_fast).
+struct StemPixels {
+  float f[4][4];   // [channel lane][pixel]; missing channels / out-of-image pixels stay 0
+  uint32_t inside; // bit j: pixel j lies inside the image
+};
+
+template <bool VEC2, int CC = 0>   // CC > 0: channel count known at compile time (fewer live registers)
+__device__ __forceinline__ void stem_sp_load(StemPixels& sp, const float* __restrict__ x, int img, int y, int sx, int c_rt,
+                                             int h, int w, int pad) {
+  const int c = CC > 0 ? CC : c_rt;
+  const int row = y - pad;
+  sp.inside = 0;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sp.f[ch][j] = 0.f;
+  if (row < 0 || row >= h) return;
+  const int64_t plane = (int64_t)h * w;
+  const int col0 = sx * 4 - pad;
+  const float* src = x + ((int64_t)img * c * h + row) * w + col0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (col0 + j >= 0 && col0 + j < w) sp.inside |= 1u << j;
+  if (VEC2) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < c) {
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          if (sp.inside & (1u << j)) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(src + ch * plane + j));
+            sp.f[ch][j] = v.x; sp.f[ch][j + 1] = v.y;
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      if (ch < c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (sp.inside & (1u << j)) sp.f[ch][j] = __ldg(src + ch * plane + j);
+  }
+}
+
+template <bool FAST, int CC = 0>
+__device__ __forceinline__ uint4 stem_sp_quant(const StemPixels& sp, int c_rt, float scale, float zpf, uint32_t zp,
+                                               float fast_lim) {
+  const int c = CC > 0 ? CC : c_rt;
+  const uint32_t zp4 = zp * 0x01010101u;
+  uint32_t wd[4] = {zp4, zp4, zp4, zp4};
+  if (sp.inside == 0) return make_uint4(zp4, zp4, zp4, zp4);
+  int q[4][4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[ch][j] = (int)zp;
+  bool done = false;
+  if (FAST) {
+    float amax = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fabsf(sp.f[ch][j]));
+    if (amax < fast_lim) {
+      const QuantFast2 qc = make_quant_fast2(scale, __frcp_rn(scale), zpf);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < c) {
+          quant2_fast(sp.f[ch][0], sp.f[ch][1], qc, q[ch][0], q[ch][1]);
+          quant2_fast(sp.f[ch][2], sp.f[ch][3], qc, q[ch][2], q[ch][3]);
+        }
+      }
+      done = true;
+    }
+  }
+  if (!done) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      if (ch < c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[ch][j] = (int)quant_u8_wrap(sp.f[ch][j], scale, zpf);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (sp.inside & (1u << j)) wd[j] = pack_low_bytes(q[0][j], q[1][j], q[2][j], q[3][j]);
+  return make_uint4(wd[0], wd[1], wd[2], wd[3]);
+}
+
+template <bool VEC2, bool FAST>
+__device__ __forceinline__ uint4 stem_superpixel(const float* __restrict__ x, int img, int y, int sx, int c, int h,
+                                                 int w, int pad, float scale, float zpf, uint32_t zp,
+                                                 float fast_lim) {
+  StemPixels sp;
+  stem_sp_load<VEC2>(sp, x, img, y, sx, c, h, w, pad);
+  return stem_sp_quant<FAST>(sp, c, scale, zpf, zp, fast_lim);
+}
+
+// The whole bordered stem image in one pass (used when the stem kernel cannot fuse the quantise).
+// One thread per superpixel; grid.y = image, so the only per-thread division is a 32-bit one.
+template <bool VEC2, bool FAST>
+__global__ void __launch_bounds__(256) stem_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs,
+                                                            int c, int h, int w, int pad, int hp, int wsp,
+                                                            float scale, float zpf, uint32_t zp, float fast_lim,
+                                                            const float* const* __restrict__ xslot) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (xslot) x = *xslot;   // run-time source address (CUDA-graph replay on a new input buffer)
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= (uint32_t)(hp * wsp)) return;
+  const int img = blockIdx.y;
+  const int y = (int)(idx / (uint32_t)wsp), sx = (int)(idx - (uint32_t)y * (uint32_t)wsp);
+  const uint4 v = stem_superpixel<VEC2, FAST>(x, img, y, sx, c, h, w, pad, scale, zpf, zp, fast_lim);
+  *reinterpret_cast<uint4*>(xs + (((int64_t)img * hp + y) * wsp + sx) * 16) = v;
+}
+
 // ---- stem2: smem-resident stem rows, sliding windows expressed by overlapping descriptors ---
 // For stride-4 stems the window of output pixel q starts at superpixel q, i.e. 16 bytes after
 // the window of q-1: exactly the fixed row pitch of a NO-SWIZZLE K-major UMMA core matrix
@@ -772,10 +916,23 @@ struct Stem2Params {
   int stages;
   int dbg;          // dev-only bottleneck probes (I8IE_STEM2_DBG): 1 = no epilogue, 2 = no MMA, 4 = no loads, 8 = no stores
   const uint8_t* xs;
+  // fused input quantise (FQ kernels): the fp32 NCHW image, read directly by the producer warps
+  const float* xf;
+  const float* const* xslot;
+  int c, h, w, pad;
+  float in_scale, fast_lim;
+  int in_zp;
+  int f_stages, f_stage_bytes;   // fp32 row ring: [rows_per_tile][c][w] floats per stage
 };
 
-template <int BN, int KH>   // KH > 0: filter height known at compile time (fully unrolled issue loop)
-__global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
+// FQ: the input quantise is fused. Warp 0 bulk-copies the raw fp32 image rows of a tile
+// (cp.async.bulk, one row of one channel plane per copy) into a second shared-memory ring, 8
+// converter warps quantise them into superpixel rows of the operand ring (generic-proxy stores +
+// fence.proxy.async), so the global-load latency hides behind the ring and the bordered u8 stem
+// image is never materialised: 21 MB written + 39 MB re-read per 100 images disappear, and so does
+// the stem_quantize launch.
+template <int BN, int KH, bool FQ>   // KH > 0: filter height known at compile time (fully unrolled issue loop)
+__global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(const __grid_constant__ CUtensorMap tmB,
                                                                const TcParams p, const Stem2Params sp) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
@@ -784,22 +941,32 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
   const int a_stage = 4 * sp.nsl * 1024;
   uint8_t* sW = smem;
   uint8_t* sA = smem + w_bytes;
-  TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(sA + (size_t)sp.stages * a_stage);
+  uint8_t* sF = sA + (size_t)sp.stages * a_stage;   // FQ: fp32 row ring
+  TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(sF + (FQ ? (size_t)sp.f_stages * sp.f_stage_bytes : 0));
   uint64_t* w_full = &ctl->full[kMaxStages - 1];   // the ring never uses more than kMaxStages-1 slots here
+  uint64_t* f_full = &ctl->full[kStemFBar];        // fp32 ring barriers (operand ring: slots < kStemFBar)
+  uint64_t* f_empty = &ctl->empty[kStemFBar];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = sp.n_img * sp.pairs;
+  constexpr int kEpiW = stem_epi_warps<BN, FQ>();                  // epilogue warps: 2 .. 2 + kEpiW
+  constexpr int kProdW = FQ ? kStemProdWarps : 0;                  // producer warps (FQ): the rest
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < sp.stages; ++s) {
-      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->full[s], FQ ? kProdW : 1);
       ptx::mbar_init(&ctl->empty[s], 1);
     }
     ptx::mbar_init(w_full, 1);
+    if (FQ)
+      for (int s = 0; s < sp.f_stages; ++s) {
+        ptx::mbar_init(&f_full[s], 1);
+        ptx::mbar_init(&f_empty[s], kProdW);
+      }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
-      ptx::mbar_init(&ctl->tmem_empty[b], kStemEpiWarps);
+      ptx::mbar_init(&ctl->tmem_empty[b], kEpiW);
     }
     ptx::fence_barrier_init();
   }
@@ -810,6 +977,13 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
   const uint32_t tmem_base = ctl->tmem_slot;
   pdl_wait();
   const int rows_per_tile = sp.kh + 4;
+  // Tile sequence of this CTA. FQ: one contiguous run of tiles, so that consecutive tiles of an image
+  // share their overlapping kh - 4 rows (copied inside shared memory instead of loaded and quantised
+  // again); otherwise static striding.
+  const int t_begin = FQ ? (int)((long long)blockIdx.x * num_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_end = FQ ? (int)((long long)(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
+  const int t_step = FQ ? 1 : (int)gridDim.x;
+  const int i_new = sp.kh > 4 ? sp.kh - 4 : 0;   // FQ: first tile row a follow-up tile has to produce itself
   const uint32_t row_bytes = (uint32_t)sp.wsp * 16;
 
   if (warp == 0) {
@@ -821,7 +995,37 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
     }
     uint32_t it = 0;
     bool alive = true;
-    for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++it) {
+    if (FQ) {
+      // fp32 rows of the tile -> fp32 ring; rows above / below the image are skipped (the converter
+      // warps emit zero-point rows for them)
+      const float* xf = sp.xslot ? *sp.xslot : sp.xf;
+      const uint32_t frow_bytes = (uint32_t)sp.w * 4;
+      const int ncopies = rows_per_tile * sp.c;
+      for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
+        const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
+        const uint32_t s = it % (uint32_t)sp.f_stages;
+        const uint32_t ph = (it / (uint32_t)sp.f_stages) & 1;
+        if (!ptx::mbar_wait(&f_empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+        const int r0 = 4 * p0 - sp.pad;                 // image row of tile row 0
+        int lo = r0 < 0 ? -r0 : 0, hi = sp.h - r0;      // tile rows [lo, hi) lie inside the image
+        if (hi > rows_per_tile) hi = rows_per_tile;
+        const bool first = tile == t_begin || p0 == 0;  // no previous tile of the same image in this CTA
+        if (!first && lo < i_new) lo = i_new;           // rows below i_new are carried over by the converters
+        if (hi < lo) hi = lo;
+        if (lane == 0) ptx::mbar_arrive_expect_tx(&f_full[s], (uint32_t)((hi - lo) * sp.c) * frow_bytes);
+        uint8_t* st = sF + (size_t)s * sp.f_stage_bytes;
+        for (int idx = lane; idx < ncopies; idx += 32) {
+          const int i = idx / sp.c, ch = idx - i * sp.c;
+          if (i < lo || i >= hi) continue;
+          ptx::bulk_load_1d(st + (size_t)idx * frow_bytes,
+                            xf + (((int64_t)img * sp.c + ch) * sp.h + (r0 + i)) * sp.w, frow_bytes, &f_full[s]);
+        }
+        __syncwarp();
+      }
+      alive = false;
+    }
+
+    for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
       const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
       const uint32_t s = it % (uint32_t)sp.stages;
       const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
@@ -853,7 +1057,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
     bool alive = ptx::mbar_wait(w_full, 0);
     if (!alive) atomicCAS(&g_tc_error, 0, 5);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles && alive; tile += gridDim.x, ++it) {
+    for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
       const uint32_t buf = it & 1, bph = (it >> 1) & 1;
       const uint32_t s = it % (uint32_t)sp.stages;
       const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
@@ -893,18 +1097,135 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
       ptx::mbar_arrive(&ctl->tmem_full[0]);
       ptx::mbar_arrive(&ctl->tmem_full[1]);
     }
+  } else if (FQ && warp >= 2 + kEpiW) {
+    // ===== converter warps (fused quantise): fp32 ring -> u8 superpixel rows in the operand ring.
+    // Rows a tile shares with its predecessor (same image, same CTA) are copied from the previous
+    // operand stage; of the new rows, warp pw takes every kProdW-th, and a lane owns superpixels
+    // lane and lane + 32 (wsp <= 64), processed together for instruction-level parallelism.
+    // RGB, even pad / width (two float2 per channel plane and superpixel). =====
+    const int pw = warp - 2 - kEpiW;
+    const float zpf = (float)sp.in_zp;
+    const QuantFast2 qc = make_quant_fast2(sp.in_scale, __frcp_rn(sp.in_scale), zpf);
+    const uint32_t zp4 = (uint32_t)sp.in_zp * 0x01010101u;
+    const uint32_t sA_u = ptx::smem_u32(sA), sF_u = ptx::smem_u32(sF);
+    // per-lane column state of the two superpixels (same for every row)
+    bool in01[2], in23[2], sx_ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int sx = lane + 32 * u;
+      const int col0 = sx * 4 - sp.pad;
+      sx_ok[u] = sx < sp.wsp;
+      in01[u] = sx_ok[u] && col0 >= 0 && col0 < sp.w;            // pixels 0,1 (pad and w are even)
+      in23[u] = sx_ok[u] && col0 + 2 >= 0 && col0 + 2 < sp.w;    // pixels 2,3
+    }
+    uint32_t it = 0;
+    bool dead = false;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
+      const int p0 = (tile % sp.pairs) * 2;
+      const uint32_t s = it % (uint32_t)sp.stages;
+      const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
+      const uint32_t fs = it % (uint32_t)sp.f_stages;
+      const uint32_t fph = (it / (uint32_t)sp.f_stages) & 1;
+      const int i0 = 4 * p0;
+      int nrows = sp.hp - i0;
+      if (nrows > rows_per_tile) nrows = rows_per_tile;
+      const bool first = tile == t_begin || p0 == 0;
+      // (a timed-out warp keeps walking the loop without waiting, so that nobody hangs in bar.sync)
+      if (!dead && !ptx::mbar_wait(&f_full[fs], fph)) { atomicCAS(&g_tc_error, 0, 6); dead = true; }
+      if (!dead && !ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); dead = true; }
+      // every converter warp is done with the previous tile: its rows can be read, and the stage
+      // before it (this tile's target) is no longer being read by a slower warp's copy
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kProdW) : "memory");
+      const uint32_t st = sA_u + s * (uint32_t)a_stage;
+      const uint32_t sf = sF_u + fs * (uint32_t)sp.f_stage_bytes;
+      int i_start = 0;
+      if (!first) {
+        // tile row i is row i + 8 of the previous tile: same region (i & 3), two 1 KB slots further on
+        const uint32_t sprev = sA_u + ((it - 1) % (uint32_t)sp.stages) * (uint32_t)a_stage;
+        for (int i = pw; i < i_new; i += kProdW) {
+          const uint32_t off = (uint32_t)((i & 3) * sp.nsl + (i >> 2)) * 1024u;
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (sx_ok[u]) ptx::sts128(st + off + (uint32_t)(lane + 32 * u) * 16u,
+                                      ptx::lds128(sprev + off + 2048u + (uint32_t)(lane + 32 * u) * 16u));
+        }
+        i_start = i_new;
+      }
+      for (int i = i_start + pw; i < nrows; i += kProdW) {
+        const int row = i0 + i - sp.pad;
+        const bool row_ok = row >= 0 && row < sp.h;
+        const uint32_t rp = sf + (uint32_t)((i * 3 * sp.w - sp.pad) * 4);   // channel plane 0 of tile row i, bordered column 0
+        const uint32_t drow = st + (uint32_t)((i & 3) * sp.nsl + (i >> 2)) * 1024u;
+        float2 v[2][3][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const uint32_t src = rp + (uint32_t)((ch * sp.w + (lane + 32 * u) * 4) * 4);
+            v[u][ch][0] = (row_ok && in01[u]) ? ptx::lds64_f2(src) : make_float2(0.f, 0.f);
+            v[u][ch][1] = (row_ok && in23[u]) ? ptx::lds64_f2(src + 8) : make_float2(0.f, 0.f);
+          }
+        float amax = 0.f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch)
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v[u][ch][0].x), fabsf(v[u][ch][0].y))),
+                         fmaxf(fabsf(v[u][ch][1].x), fabsf(v[u][ch][1].y)));
+        int q[2][3][4];
+        if (amax < sp.fast_lim) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              quant2_fast(v[u][ch][0].x, v[u][ch][0].y, qc, q[u][ch][0], q[u][ch][1]);
+              quant2_fast(v[u][ch][1].x, v[u][ch][1].y, qc, q[u][ch][2], q[u][ch][3]);
+            }
+        } else {   // also taken for NaN (the compare is false)
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              q[u][ch][0] = (int)quant_u8_wrap(v[u][ch][0].x, sp.in_scale, zpf);
+              q[u][ch][1] = (int)quant_u8_wrap(v[u][ch][0].y, sp.in_scale, zpf);
+              q[u][ch][2] = (int)quant_u8_wrap(v[u][ch][1].x, sp.in_scale, zpf);
+              q[u][ch][3] = (int)quant_u8_wrap(v[u][ch][1].y, sp.in_scale, zpf);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t wd[4] = {zp4, zp4, zp4, zp4};
+          if (row_ok && in01[u]) {
+            wd[0] = pack_low_bytes(q[u][0][0], q[u][1][0], q[u][2][0], sp.in_zp);
+            wd[1] = pack_low_bytes(q[u][0][1], q[u][1][1], q[u][2][1], sp.in_zp);
+          }
+          if (row_ok && in23[u]) {
+            wd[2] = pack_low_bytes(q[u][0][2], q[u][1][2], q[u][2][2], sp.in_zp);
+            wd[3] = pack_low_bytes(q[u][0][3], q[u][1][3], q[u][2][3], sp.in_zp);
+          }
+          if (sx_ok[u]) ptx::sts128(drow + (uint32_t)(lane + 32 * u) * 16u, make_uint4(wd[0], wd[1], wd[2], wd[3]));
+        }
+      }
+      // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&ctl->full[s]);
+        ptx::mbar_arrive(&f_empty[fs]);
+      }
+    }
   } else {
     const int quad = warp & 3;
     const int et = threadIdx.x - 64;
     const float rcp = __frcp_rn(p.ep.sc);
     // per-channel offsets are the same for every tile (single N tile)
-    for (int j = et; j < BN; j += 32 * kStemEpiWarps) {
+    for (int j = et; j < BN; j += 32 * kEpiW) {
       ctl->oc[0][j] = (j < p.N) ? __ldg(p.ep.oc + j) : 0;
       ctl->bias[0][j] = 0.f;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kStemEpiWarps) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiW) : "memory");
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
       const uint32_t buf = it & 1, bph = (it >> 1) & 1;
       const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
       const int l = quad * 32 + lane;            // TMEM lane = tile row
@@ -916,11 +1237,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) tc_stem2_kernel(const __grid_
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
       if (!(sp.dbg & 1)) {
-        epilogue_row<BN, kStemEpiWarps / 4>(p, t_row, (ok && !(sp.dbg & 8)) ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]),
-                                            ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2);
+        epilogue_row<BN, kEpiW / 4>(p, t_row, (ok && !(sp.dbg & 8)) ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]),
+                                    ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2);
         // output pitch wider than the N tile (e.g. 96 channels stored at pitch 128): the pad lanes
         // carry the zero point; written by the warp of each pair that had fewer chunks
-        if (BN < p.out_cp && ((warp - 2) >> 2) == ((BN / 32) % (kStemEpiWarps / 4)) && ok && m >= 0) {
+        if (BN < p.out_cp && ((warp - 2) >> 2) == ((BN / 32) % (kEpiW / 4)) && ok && m >= 0) {
           const uint32_t z4 = (uint32_t)p.ep.zp_out * 0x01010101u;
           for (int c = BN; c < p.out_cp; c += 16)
             *reinterpret_cast<uint4*>(p.y + (size_t)m * p.out_cp + c) = make_uint4(z4, z4, z4, z4);
@@ -995,95 +1316,6 @@ __global__ void stem_pack_kernel(const uint8_t* __restrict__ x, uint8_t* __restr
     }
     *reinterpret_cast<uint4*>(xs + t * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
   }
-}
-
-// Same layout, produced straight from the fp32 NCHW image with the input quantise
-// (quantize_utils.cc:44-52) fused in. One thread per superpixel (4 px x 4 lanes = one 128-bit
-// store); grid.y = image, so the only per-thread division is a 32-bit one.
-// VEC2: pad and w even -> the 4 pixels are two aligned float2 per channel plane.
-// FAST: packed fp32x2 quantise behind one magnitude test per thread (quant2_fast).
-template <bool VEC2, bool FAST>
-__global__ void __launch_bounds__(256) stem_quantize_kernel(const float* __restrict__ x, uint8_t* __restrict__ xs,
-                                                            int c, int h, int w, int pad, int hp, int wsp,
-                                                            float scale, float zpf, uint32_t zp, float fast_lim,
-                                                            const float* const* __restrict__ xslot) {
-  pdl_launch_dependents();
-  pdl_wait();
-  if (xslot) x = *xslot;   // run-time source address (CUDA-graph replay on a new input buffer)
-  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
-  if (idx >= (uint32_t)(hp * wsp)) return;
-  const int img = blockIdx.y;
-  const int y = (int)(idx / (uint32_t)wsp), sx = (int)(idx - (uint32_t)y * (uint32_t)wsp);
-  const int row = y - pad;
-  const uint32_t zp4 = zp * 0x01010101u;
-  uint32_t wd[4] = {zp4, zp4, zp4, zp4};
-  const uint64_t pol = l2_evict_first_policy();   // the fp32 image is read once: keep weights/activations in L2
-  if (row >= 0 && row < h) {
-    const int64_t plane = (int64_t)h * w;
-    const int col0 = sx * 4 - pad;
-    const float* src = x + ((int64_t)img * c * h + row) * w + col0;
-    float f[4][4];   // [channel lane][pixel]
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[ch][j] = 0.f;
-    if (VEC2) {
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < c) {
-#pragma unroll
-          for (int j = 0; j < 4; j += 2) {
-            if (col0 + j >= 0 && col0 + j < w) {
-              const float2 v = __ldg(reinterpret_cast<const float2*>(src + ch * plane + j));
-              f[ch][j] = v.x; f[ch][j + 1] = v.y;
-            }
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        if (ch < c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col0 + j >= 0 && col0 + j < w) f[ch][j] = __ldg(src + ch * plane + j);
-    }
-    int q[4][4];
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) q[ch][j] = (int)zp;
-    bool done = false;
-    if (FAST) {
-      float amax = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fabsf(f[ch][j]));
-      if (amax < fast_lim) {
-        const QuantFast2 qc = make_quant_fast2(scale, __frcp_rn(scale), zpf);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < c) {
-            quant2_fast(f[ch][0], f[ch][1], qc, q[ch][0], q[ch][1]);
-            quant2_fast(f[ch][2], f[ch][3], qc, q[ch][2], q[ch][3]);
-          }
-        }
-        done = true;
-      }
-    }
-    if (!done) {
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        if (ch < c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) q[ch][j] = (int)quant_u8_wrap(f[ch][j], scale, zpf);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (col0 + j >= 0 && col0 + j < w) wd[j] = pack_low_bytes(q[0][j], q[1][j], q[2][j], q[3][j]);
-  }
-  *reinterpret_cast<uint4*>(xs + (((int64_t)img * hp + y) * wsp + sx) * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
 }
 
 // stem weights: ws[n][r][64], lane j = 4*px + ch
@@ -1337,7 +1569,6 @@ int launch_pair_strip_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParam
   const int ctl_bytes = (int)sizeof(TcControlS<BN>);
   const int kSubBh = (BN / 2) * 128;
   p.stages_a = 3;
-  p.strip_bo = std::getenv("I8IE_STRIP_BO") != nullptr ? std::atoi(std::getenv("I8IE_STRIP_BO")) : 0;
   int stages = (kMaxSmem - 1024 - ctl_bytes - p.stages_a * kStripBytes) / kSubBh;
   if (stages > kMaxStages) stages = kMaxStages;
   I8IE_REQUIRE(stages >= 3, "tcgen05 strip pair: no room for a pipeline");
@@ -1415,6 +1646,7 @@ int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* ta
 }
 
 int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn) {
+  tc_apply_wait_hint();
   return encode_tiled_2d(tm, w, (uint64_t)ldw, (uint64_t)rows, (uint64_t)ldw, bk, bn);
 }
 
@@ -1639,50 +1871,80 @@ bool tc_stem2_eligible(const GemmGeom& g, int c) {
 }
 
 template <int BN>
-int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const CUtensorMap& tmB, TcParams p,
-                    cudaStream_t stream) {
-  Stem2Params sp;
+int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const StemF32Src* f32,
+                    const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
+  Stem2Params sp{};
   sp.n_img = g.n; sp.oh = g.oh; sp.ow = g.ow; sp.kh = g.kh; sp.hp = s.hp; sp.wsp = s.wsp;
   sp.pairs = (g.oh + 1) / 2;
   sp.nsl = (g.kh + 4 + 3) / 4;
   sp.xs = xs;
+  const bool fq = f32 != nullptr;
+  if (fq) {
+    sp.xf = f32->x; sp.xslot = f32->xslot; sp.c = s.c; sp.h = g.h; sp.w = g.w; sp.pad = g.pad;
+    sp.in_scale = f32->scale; sp.in_zp = f32->zp; sp.fast_lim = quant_fast_limit(f32->scale);
+  }
   sp.dbg = 0;
   if (const char* e = std::getenv("I8IE_STEM2_DBG")) sp.dbg = std::atoi(e);
 
   const int w_bytes = g.kh * BN * 64;
   const int a_stage = 4 * sp.nsl * 1024;
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
-  int stages = (227 * 1024 - 1024 - ctl_bytes - w_bytes) / a_stage;
-  if (stages > 6) stages = 6;
-  I8IE_REQUIRE(stages >= 2, "stem2: not enough shared memory for the row ring");
+  const int budget = 227 * 1024 - 1024 - ctl_bytes - w_bytes;
+  int stages, smem;
+  if (fq) {
+    // two operand stages (a tile's MMAs are short), the rest of shared memory is the fp32 row ring
+    stages = 2;
+    sp.f_stage_bytes = (((g.kh + 4) * s.c * g.w * 4) + 127) & ~127;
+    sp.f_stages = (budget - stages * a_stage) / sp.f_stage_bytes;
+    if (sp.f_stages > kMaxStages - 1 - kStemFBar) sp.f_stages = kMaxStages - 1 - kStemFBar;
+    I8IE_REQUIRE(sp.f_stages >= 2, "stem2: not enough shared memory for the fp32 row ring");
+    smem = w_bytes + stages * a_stage + sp.f_stages * sp.f_stage_bytes + ctl_bytes + 1024;
+  } else {
+    stages = budget / a_stage;
+    if (stages > 6) stages = 6;
+    I8IE_REQUIRE(stages >= 2, "stem2: not enough shared memory for the row ring");
+    smem = w_bytes + stages * a_stage + ctl_bytes + 1024;
+  }
   sp.stages = stages;
-  const int smem = w_bytes + stages * a_stage + ctl_bytes + 1024;
   static int attr_smem = 0;
-  auto kern = g.kh == 11 ? tc_stem2_kernel<BN, 11> : g.kh == 7 ? tc_stem2_kernel<BN, 7> : tc_stem2_kernel<BN, 0>;
+  auto kern = fq ? (g.kh == 11 ? tc_stem2_kernel<BN, 11, true> : tc_stem2_kernel<BN, 0, true>)
+                 : (g.kh == 11 ? tc_stem2_kernel<BN, 11, false> : tc_stem2_kernel<BN, 0, false>);
   if (attr_smem < smem) {
-    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    I8IE_CUDA_OK(cudaFuncSetAttribute(tc_stem2_kernel<BN, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
   const int tiles = sp.n_img * sp.pairs;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_pdl(kern, dim3(grid), dim3(kStemThreads), (size_t)smem, stream, tmB, p, sp);
+  const int threads = fq ? stem_threads<BN, true>() : stem_threads<BN, false>();
+  launch_pdl(kern, dim3(grid), dim3(threads), (size_t)smem, stream, tmB, p, sp);
   return check_launch("tc_stem2_kernel");
 }
 
-int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const CUtensorMap& tmB, int bn,
-                    uint8_t* y, const EpiParams& ep, cudaStream_t stream) {
+// The quantise can be fused into the stem kernel when its fast path applies: RGB, even pad (float2
+// reads of the staged rows), image rows that are whole 16-byte units from a 16-byte aligned source
+// (bulk copies; slot sources are allocator-aligned), two fp32 tile stages fit, mid-range scale.
+bool tc_stem2_can_fuse_quantize(const GemmGeom& g, int c, const float* x, const float* const* xslot, float scale) {
+  if (std::getenv("I8IE_NO_STEM_FUSEQ") != nullptr) return false;
+  const int f_stage = (g.kh + 4) * c * g.w * 4;
+  return c == 3 && (g.pad % 2 == 0) && (g.w % 4 == 0) && (xslot || (reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+         2 * f_stage <= 100 * 1024 && quant_fast_limit(scale) > 0.f;
+}
+
+int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const StemF32Src* f32,
+                    const CUtensorMap& tmB, int bn, uint8_t* y, const EpiParams& ep, cudaStream_t stream) {
   TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
   I8IE_REQUIRE(bn % 32 == 0 || bn >= g.out_cp, "stem2: N tile %d narrower than the output pitch must be a multiple of 32", bn);
   switch (bn) {
-    case 32:  return launch_stem2_bn<32>(g, s, xs, tmB, p, stream);
-    case 64:  return launch_stem2_bn<64>(g, s, xs, tmB, p, stream);
-    case 96:  return launch_stem2_bn<96>(g, s, xs, tmB, p, stream);
-    case 128: return launch_stem2_bn<128>(g, s, xs, tmB, p, stream);
+    case 32:  return launch_stem2_bn<32>(g, s, xs, f32, tmB, p, stream);
+    case 64:  return launch_stem2_bn<64>(g, s, xs, f32, tmB, p, stream);
+    case 96:  return launch_stem2_bn<96>(g, s, xs, f32, tmB, p, stream);
+    case 128: return launch_stem2_bn<128>(g, s, xs, f32, tmB, p, stream);
   }
   set_error("stem2: unsupported BN %d", bn);
   return I8IE_EINVAL;

@@ -77,6 +77,56 @@ def test_tc_conv(geom):
     assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
 
 
+PAIR = [  # shapes served by the CTA-pair kernel (cp % 128 == 0, N tile 128 / 192 / 256): n, c, h, w, kc, k, stride, pad
+    (1, 128, 5, 5, 128, 3, 1, 1),        # one M tile: the odd CTA of the pair only lends its weight half
+    (3, 128, 13, 13, 128, 3, 2, 0),      # stride 2, no padding, N tile 128
+    (5, 256, 13, 13, 384, 3, 1, 1),      # 7 M tiles (odd) x 2 N tiles of 192
+    (9, 96, 27, 27, 256, 5, 1, 2),       # 52 M tiles, pad 2, pitch-128 input with 96 real channels
+    (2, 128, 16, 16, 500, 1, 1, 0),      # 1x1, N = 500 -> two N tiles of 256 with a ragged tail
+    (4, 384, 7, 9, 192, 3, 1, 2),        # pad 2 with a 3x3 filter, 3 channel blocks
+]
+
+
+def _run_conv_parity(geom):
+    n, c, h, w_, kc, k, s, p = geom
+    rng = np.random.default_rng(sum(geom) + 1)
+    a = np.sqrt(6.0 / (c * k * k))
+    w = rng.uniform(-a, a, size=(kc, c, k, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(kc,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(n, c, h, w_), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0293), int(rng.integers(1, 256))
+    out_scale, out_zp = np.float32(0.061), int(rng.integers(60, 190))
+    L = make_layer("conv", w, b, (out_scale, out_zp), s, p)
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.conv2d_u8(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    oh, ow = exp.shape[2], exp.shape[3]
+    acc = torch.empty(n * oh * ow * kc, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    _no_tc_error()
+    assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    raw = out.buf.cpu().numpy().reshape(n * oh * ow, -1)
+    assert np.all(raw[:, kc:] == out_zp)          # pad lanes of the output pitch carry the zero point
+    L.fuse_relu = True
+    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=2)
+    assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
+
+
+@pytest.mark.parametrize("geom", PAIR)
+def test_tc_conv_cta_pair(geom):
+    """tcgen05.mma.cta_group::2 kernel (two SMs per 256-row tile)."""
+    _run_conv_parity(geom)
+
+
+@pytest.mark.parametrize("variant", ["I8IE_NO_CLUSTER", "I8IE_CLUSTER_MC", "I8IE_STRIP"])
+@pytest.mark.parametrize("geom", [PAIR[2], PAIR[3], PAIR[5]])
+def test_tc_conv_cluster_variants(geom, variant, monkeypatch):
+    """The opt-in variants of the same layers stay bit-exact: single CTAs, 2-CTA clusters with the
+    weight tile multicast, and the stride-1 A-strip pair kernel (taps walked by descriptor offsets)."""
+    monkeypatch.setenv(variant, "1")
+    _run_conv_parity(geom)
+
+
 def test_tc_ineligible_shapes_are_refused_when_forced():
     rng = np.random.default_rng(0)
     w = rng.uniform(-0.3, 0.3, size=(8, 3, 3, 3)).astype(np.float32)   # cp = 16: not a 32-byte K block
@@ -130,3 +180,45 @@ def test_tc_stem_conv(geom):
     exp3 = port.conv2d_u8(q3, qw, qb, s, p, np.float32(0.031), 90, ws, out_scale, out_zp)
     out3 = L._forward_u8(u8_tensor_from_nchw(q3, 0.031, 90), impl=0)
     assert np.array_equal(out3.numpy(), exp3)
+
+
+STEM_FQ = [  # RGB stride-4 stems whose rows are whole 16-byte units: the stem kernel quantises the fp32 image itself
+    (3, 3, 64, 64, 64, 11, 4, 2), (5, 3, 100, 96, 96, 11, 4, 2), (2, 3, 52, 48, 32, 7, 4, 2),
+    (150, 3, 32, 32, 16, 11, 4, 2),     # 600 tiles: both shared-memory rings wrap several times per SM
+    (2, 3, 224, 224, 96, 11, 4, 0),     # no padding
+]
+
+
+@pytest.mark.parametrize("geom", STEM_FQ)
+@pytest.mark.parametrize("wild", [False, True])
+def test_tc_stem_fused_quantize(geom, wild):
+    """i8ie_conv2d_f32_u8 with the quantise fused into the stem kernel (fp32 rows bulk-copied to shared
+    memory, quantised by converter warps): same bits as quantize() followed by the u8 conv, including
+    out-of-range / non-finite pixels (x86 cast semantics of quantize_utils.cc:44-52)."""
+    from int8inferenceengine_b200 import backend as B
+    n, c, h, w_, kc, k, s, p = geom
+    rng = np.random.default_rng(sum(geom) + 7)
+    a = np.sqrt(6.0 / (c * k * k))
+    w = rng.uniform(-a, a, size=(kc, c, k, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(kc,)).astype(np.float32)
+    x = rng.uniform(-3.1, 3.1, size=(n, c, h, w_)).astype(np.float32)
+    if wild:
+        flat = x.reshape(-1)
+        idx = rng.choice(flat.size, size=min(4000, flat.size // 8), replace=False)
+        flat[idx] = rng.choice(np.array([np.nan, np.inf, -np.inf, 1e30, -1e30, 7.5, -9.25, 3.0e9, -4.0e9, 1e-30, -0.0],
+                                        np.float32), size=idx.size)
+    in_scale, in_zp = np.float32(0.025), 127
+    out_scale, out_zp = np.float32(0.0518), 116
+    q = port.quantize(x, in_scale, in_zp)
+    L = make_layer("conv", w, b, (out_scale, out_zp), s, p)
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.conv2d_u8(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    oh, ow = exp.shape[2], exp.shape[3]
+    acc = torch.zeros(n * oh * ow * kc, dtype=torch.int32, device="cuda")
+    out = L.forward_quantize_fused(B.tensor(x), in_scale, in_zp, acc_out=acc)
+    _no_tc_error()
+    assert out is not None
+    assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    raw = out.buf.cpu().numpy().reshape(n * oh * ow, -1)
+    assert np.all(raw[:, kc:] == out_zp)
