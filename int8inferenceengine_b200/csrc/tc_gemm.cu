@@ -31,19 +31,6 @@ namespace i8ie {
 
 __device__ int g_tc_error = 0;  // first protocol error seen by any tensor-core kernel (0 = none)
 
-constexpr uint32_t kDefaultWaitHintNs = 0;
-// dev knob: I8IE_WAIT_HINT=<ns> sets the mbarrier suspend-time hint of every tensor-core kernel
-// (set once, when the first tensor map of the process is encoded: never inside a graph capture)
-static void tc_apply_wait_hint() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  uint32_t v = kDefaultWaitHintNs;
-  if (const char* e = std::getenv("I8IE_WAIT_HINT")) v = (uint32_t)std::atoi(e);
-  cudaMemcpyToSymbol(ptx::g_wait_hint_ns, &v, sizeof(v));
-}
-
-
 struct TcParams {
   int M, N, out_cp;
   int tiles_m, tiles_n;
@@ -914,7 +901,7 @@ struct Stem2Params {
   int pairs;        // ceil(oh / 2) output-row pairs per image
   int nsl;          // 1 KB slots per region = ceil((kh + 4) / 4)
   int stages;
-  int dbg;          // dev-only bottleneck probes (I8IE_STEM2_DBG): 1 = no epilogue, 2 = no MMA, 4 = no loads, 8 = no stores
+  int dbg;          // dev-only bottleneck probes (I8IE_STEM2_DBG): 1 = no epilogue, 2 = no MMA, 4 = no loads, 8 = no stores, 16 = no quantise
   const uint8_t* xs;
   // fused input quantise (FQ kernels): the fp32 NCHW image, read directly by the producer warps
   const float* xf;
@@ -1000,7 +987,6 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       // warps emit zero-point rows for them)
       const float* xf = sp.xslot ? *sp.xslot : sp.xf;
       const uint32_t frow_bytes = (uint32_t)sp.w * 4;
-      const int ncopies = rows_per_tile * sp.c;
       for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
         const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
         const uint32_t s = it % (uint32_t)sp.f_stages;
@@ -1012,14 +998,14 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         const bool first = tile == t_begin || p0 == 0;  // no previous tile of the same image in this CTA
         if (!first && lo < i_new) lo = i_new;           // rows below i_new are carried over by the converters
         if (hi < lo) hi = lo;
-        if (lane == 0) ptx::mbar_arrive_expect_tx(&f_full[s], (uint32_t)((hi - lo) * sp.c) * frow_bytes);
+        // NCHW: the rows [lo, hi) of one channel plane are one contiguous run -> one bulk copy per plane
+        // (stage layout [c][rows_per_tile][w] floats)
+        const uint32_t run = (sp.dbg & 4) ? 0u : (uint32_t)(hi - lo) * frow_bytes;
+        if (lane == 0) ptx::mbar_arrive_expect_tx(&f_full[s], run * (uint32_t)sp.c);
         uint8_t* st = sF + (size_t)s * sp.f_stage_bytes;
-        for (int idx = lane; idx < ncopies; idx += 32) {
-          const int i = idx / sp.c, ch = idx - i * sp.c;
-          if (i < lo || i >= hi) continue;
-          ptx::bulk_load_1d(st + (size_t)idx * frow_bytes,
-                            xf + (((int64_t)img * sp.c + ch) * sp.h + (r0 + i)) * sp.w, frow_bytes, &f_full[s]);
-        }
+        if (lane < sp.c && run != 0)
+          ptx::bulk_load_1d(st + (size_t)(lane * rows_per_tile + lo) * frow_bytes,
+                            xf + (((int64_t)img * sp.c + lane) * sp.h + (r0 + lo)) * sp.w, run, &f_full[s]);
         __syncwarp();
       }
       alive = false;
@@ -1151,17 +1137,17 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         }
         i_start = i_new;
       }
-      for (int i = i_start + pw; i < nrows; i += kProdW) {
+      for (int i = i_start + pw; i < nrows && !(sp.dbg & 16); i += kProdW) {
         const int row = i0 + i - sp.pad;
         const bool row_ok = row >= 0 && row < sp.h;
-        const uint32_t rp = sf + (uint32_t)((i * 3 * sp.w - sp.pad) * 4);   // channel plane 0 of tile row i, bordered column 0
+        const uint32_t rp = sf + (uint32_t)((i * sp.w - sp.pad) * 4);   // channel plane 0 of tile row i, bordered column 0
         const uint32_t drow = st + (uint32_t)((i & 3) * sp.nsl + (i >> 2)) * 1024u;
         float2 v[2][3][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u)
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            const uint32_t src = rp + (uint32_t)((ch * sp.w + (lane + 32 * u) * 4) * 4);
+            const uint32_t src = rp + (uint32_t)((ch * rows_per_tile * sp.w + (lane + 32 * u) * 4) * 4);
             v[u][ch][0] = (row_ok && in01[u]) ? ptx::lds64_f2(src) : make_float2(0.f, 0.f);
             v[u][ch][1] = (row_ok && in23[u]) ? ptx::lds64_f2(src + 8) : make_float2(0.f, 0.f);
           }
@@ -1646,7 +1632,6 @@ int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* ta
 }
 
 int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn) {
-  tc_apply_wait_hint();
   return encode_tiled_2d(tm, w, (uint64_t)ldw, (uint64_t)rows, (uint64_t)ldw, bk, bn);
 }
 

@@ -51,37 +51,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// try_wait with a suspend-time hint (ns): the hardware may park the warp until the phase completes
-// or the time limit passes, instead of returning to the polling loop every few dozen clocks.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
 // Bounded wait: a protocol bug must never hang the GPU. Returns false on timeout
 // (~seconds), after which the caller records an error and bails out.
-// A warp that polls takes issue slots from the warps it is waiting for (ncu on the stem kernel:
-// the 12 waiting epilogue warps issued more instructions than everything else together), so the
-// slow path parks the warp with a suspend-time hint (g_wait_hint_ns, 0 = plain polling).
-__device__ uint32_t g_wait_hint_ns = 0;
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
-  const uint32_t hint = g_wait_hint_ns;
-  if (hint == 0) {
-    while (!mbar_try_wait(bar, parity)) {
-      if (clock64() - t0 > 4000000000ll) return false;
-    }
-  } else {
-    while (!mbar_try_wait_hint(bar, parity, hint)) {
-      if (clock64() - t0 > 4000000000ll) return false;
-    }
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) return false;
   }
   return true;
 }

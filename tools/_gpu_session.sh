@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -x -q -k "stem" 2>&1 | tail -8
-python tools/stem_bench.py 2>&1 | tail -1
-I8IE_NO_STEM_FUSEQ=1 python tools/stem_bench.py 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/step_trace.py 2>&1 | tail -19
+python bench.py --no-cpu-baseline --no-hbm-kernels 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('b100', j['value'], j['ms_per_step'], j['e2e']['value'], j['gpu_launches'])"
