@@ -127,8 +127,28 @@ class Module:
 
     def __call__(self, x):
         if self.is_quant and self.graph and getattr(self, "record", None) is None and _B.graphable(x.data):
+            parts = None if self.__dict__.get("_no_chunks") else _B.pending_chunks(x.data)
+            if parts:
+                return self._call_chunked(x, parts)
             return self._call_graphed(x)
         return self._call_eager(x)
+
+    def _call_chunked(self, x, parts):
+        # Extension: the batch is still arriving from pinned host memory in row chunks
+        # (backend._ChunkedStorage). Images are independent and the quantisation parameters are
+        # per tensor, so running the chunks one after the other gives the same bits as one call
+        # while the forward of chunk k overlaps the host->device copy of chunk k+1.
+        outs = []
+        for sub, ev in parts:
+            _B.wait_event(ev)
+            outs.append(self._call_graphed(Tensor(sub)).data)
+        _B.chunks_consumed(x.data)
+        if any(not isinstance(o, _B.TensorF32) or len(o._shape) < 1 or o._shape[0] != p[0]._shape[0]
+               for o, p in zip(outs, parts)):
+            # a forward() that does not keep the batch dimension cannot be split: run it whole from now on
+            self.__dict__["_no_chunks"] = True
+            return self._call_graphed(x)
+        return Tensor(_B.concat_rows(outs))
 
     def _call_eager(self, x):
         if self.is_quant:

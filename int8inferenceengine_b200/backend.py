@@ -19,6 +19,7 @@ carried over).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 import warnings
 
@@ -103,6 +104,90 @@ class _SlotStorage:
             else:
                 raise I8ieError("graph input of %d floats is not a multiple of 16 bytes" % self.numel)
         return self._static
+
+
+class _ChunkedStorage:
+    """Storage whose bytes are still arriving from pinned host memory: `tensor()` splits a large
+    pinned batch into row chunks copied on a side stream, one event per chunk. `Module.__call__`
+    consumes the chunks one by one (the forward of chunk k overlaps the copy of chunk k+1; images
+    are independent, so the result does not depend on the split); any other access simply orders
+    the current stream behind the last copy."""
+
+    def __init__(self, t, chunks):
+        self._t = t
+        self.views = 0
+        self.chunks = chunks          # [(row_begin, row_end, event)] or None once ordered
+
+    @property
+    def t(self):
+        if self.chunks:
+            torch.cuda.current_stream().wait_event(self.chunks[-1][2])   # one copy stream: the last event covers all
+            self.chunks = None
+        return self._t
+
+
+_COPY_STREAM = None
+H2D_CHUNK_MIN_BYTES = 8 << 20      # below this a single copy is already short
+H2D_CHUNK_MIN_ROWS = 16
+
+
+def _h2d_chunks(rows, nbytes):
+    if nbytes < H2D_CHUNK_MIN_BYTES or os.environ.get("I8IE_NO_H2D_CHUNKS"):
+        return 1
+    for c in (8, 6, 5, 4, 3, 2):
+        if rows % c == 0 and rows // c >= H2D_CHUNK_MIN_ROWS:
+            return c
+    return 1
+
+
+def _tensor_from_pinned(h):
+    """Pinned host tensor -> device, as row chunks on the copy stream (see _ChunkedStorage)."""
+    global _COPY_STREAM
+    shape = list(h.shape)
+    flat = h.reshape(-1)
+    c = _h2d_chunks(shape[0], flat.numel() * 4) if len(shape) >= 2 else 1
+    if c == 1:
+        return TensorF32(_Storage(flat.to("cuda", non_blocking=True)), shape)
+    if _COPY_STREAM is None:
+        _COPY_STREAM = torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    dev = torch.empty(flat.numel(), dtype=torch.float32, device="cuda")
+    dev.record_stream(_COPY_STREAM)
+    _COPY_STREAM.wait_stream(cur)      # the block may be recycled from work still queued on this stream
+    rows = shape[0] // c
+    per = flat.numel() // shape[0]
+    chunks = []
+    with torch.cuda.stream(_COPY_STREAM):
+        for k in range(c):
+            a, b = k * rows, (k + 1) * rows
+            dev[a * per:b * per].copy_(flat[a * per:b * per], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(_COPY_STREAM)
+            chunks.append((a, b, ev))
+    return TensorF32(_ChunkedStorage(dev, chunks), shape)
+
+
+def pending_chunks(x):
+    """[(sub-batch tensor, copy-done event)] of a float tensor still arriving in chunks, else None."""
+    st = x._st
+    if not isinstance(st, _ChunkedStorage) or not st.chunks or len(x._shape) < 2 or x._shape[0] != st.chunks[-1][1]:
+        return None
+    per = st._t.numel() // x._shape[0]
+    return [(TensorF32(_Storage(st._t[a * per:b * per]), [b - a] + x._shape[1:]), ev) for a, b, ev in st.chunks]
+
+
+def wait_event(ev):
+    torch.cuda.current_stream().wait_event(ev)
+
+
+def chunks_consumed(x):
+    x._st.chunks = None
+
+
+def concat_rows(parts):
+    """Stacks per-chunk results (same trailing shape) along the batch dimension."""
+    shape = [sum(p._shape[0] for p in parts)] + parts[0]._shape[1:]
+    return TensorF32(_Storage(torch.cat([p.buf for p in parts])), shape)
 
 
 def _src_ptrs(x):
@@ -353,6 +438,8 @@ def tensor(ndarray):
     if isinstance(ndarray, torch.Tensor) and ndarray.device.type == "cpu":
         # same force-cast; a pinned f32 tensor goes to the device without a staging copy
         h = ndarray.detach().to(torch.float32).contiguous()
+        if h.is_pinned():
+            return _tensor_from_pinned(h)
         return TensorF32(_Storage(h.reshape(-1).to("cuda", non_blocking=True)), list(h.shape))
     a = np.ascontiguousarray(np.asarray(ndarray), dtype=np.float32)
     t = torch.from_numpy(a.reshape(-1).copy()).to("cuda", non_blocking=False)

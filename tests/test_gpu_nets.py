@@ -119,3 +119,28 @@ def test_graph_replay_matches_eager_on_any_input_buffer(topo, batch):
     a = m(t5).numpy()
     m(i8ie.tensor(xs[1]))
     assert np.array_equal(m(t5).numpy(), a) and np.array_equal(a, want[5])
+
+
+@pytest.mark.parametrize("topo,batch", [("mini_alex", 64), ("simple_conv", 96), ("fc_mnist", 40)])
+def test_pinned_host_batches_arrive_in_chunks(topo, batch, monkeypatch):
+    """A pinned host batch is copied in row chunks on a side stream and Module.__call__ runs the
+    chunks as they land (H2D of chunk k+1 under the forward of chunk k): same bits as one
+    whole-batch call, for the quantised forward, for calibration-side (eager fp32) access and for
+    plain .numpy()."""
+    import torch
+    from int8inferenceengine_b200 import backend as B
+    monkeypatch.setattr(B, "H2D_CHUNK_MIN_BYTES", 0)
+    sd = W.make_weights(topo, 0)
+    m = build_module(topo, sd, calib=W.make_images(topo, 100, 1))
+    xs = [W.make_images(topo, batch, 20 + i) for i in range(5)]
+    want = [m(i8ie.tensor(x)).numpy() for x in xs]               # numpy input: one blocking copy
+    for i, x in enumerate(xs):                                    # pinned input: chunked (warm-up, capture, replay)
+        t = i8ie.tensor(torch.from_numpy(x).pin_memory())
+        assert isinstance(t.data._st, B._ChunkedStorage) and len(t.data._st.chunks) > 1
+        assert np.array_equal(m(t).numpy(), want[i]), i
+        assert t.data._st.chunks is None
+    t = i8ie.tensor(torch.from_numpy(xs[0]).pin_memory())
+    assert np.array_equal(t.numpy(), xs[0])                        # any other access orders behind the copies
+    t = i8ie.tensor(torch.from_numpy(xs[1]).pin_memory())
+    v = t.reshape(batch, -1)                                       # a view of a chunked tensor is not split
+    assert np.array_equal(v.numpy(), xs[1].reshape(batch, -1))
