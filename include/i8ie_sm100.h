@@ -89,6 +89,25 @@ I8IE_API int i8ie_top1_pack(const float* logits, const int64_t* ref_argmax, int 
 I8IE_API int i8ie_top1_unpack(const void* gathered, int world, int64_t chunk_bytes, float* logits_all,
                      int64_t* agree_total, void* stream);
 
+/* ---- F1: the FP32 forward (calibration side; feeds Calibrator::sample) -------------------------
+ * Conv2d::forward_prop(Tensor<float>&&), conv2d.cc:63-98: im2col + cblas_sgemm + bias, here one
+ * implicit-GEMM fp32 FMA kernel. x dense NCHW [n,c,h,w], w OIHW [kc,c,kh,kw], bias [kc],
+ * y dense NCHW [n,kc,oh,ow], oh = (h - kh + 2*pad)/stride + 1 (conv2d.cc:71-72).
+ * minmax2 (device float[2], may be NULL): {min, max} of everything written is folded into it with
+ * atomics — the caller initialises it to {+FLT_MAX, -FLT_MAX}; this is the calibrator's range
+ * (conv2d.cc:94-96 -> calibrator.cc:6-27 at quantile 1) without a second pass over y.
+ * Parity is tolerance-only (fp32 summation order differs from MKL's, as any two sgemms do). */
+I8IE_API int i8ie_conv2d_f32(const float* x, const float* w, const float* bias, float* y, int n, int c, int h,
+                             int wd, int kc, int kh, int kw, int stride, int pad, float* minmax2, void* stream);
+/* Linear::forward_prop(Tensor<float>&&), fully_connected.cc:5-21: y[m,n] = x[m,k] . w[n,k]^T + bias. */
+I8IE_API int i8ie_linear_f32(const float* x, const float* w, const float* bias, float* y, int m, int n, int k,
+                             float* minmax2, void* stream);
+/* relu<float>, functional.cc:5-13: y = x > 0 ? x : 0. */
+I8IE_API int i8ie_relu_f32(const float* x, float* y, int64_t n, void* stream);
+/* max_pool2d<float>, functional.cc:36-64: dense NCHW, no padding, floor output size. */
+I8IE_API int i8ie_maxpool_f32_nchw(const float* x, float* y, int n, int c, int h, int w, int ksize, int stride,
+                                   void* stream);
+
 /* A5: dequantize(float*, u8*, size, scale, zp), quantize_utils.cc:38-42:
  *   x[i] = (float)((int)q[i] - zp) * scale. Flat, dense. */
 I8IE_API int i8ie_dequantize_u8_f32(const uint8_t* q, float* x, int64_t n, float scale, int zp, void* stream);

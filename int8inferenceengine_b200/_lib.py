@@ -19,6 +19,7 @@ SYMBOLS = [
     "i8ie_conv2d_plan_impl", "i8ie_conv2d_u8", "i8ie_conv2d_f32_u8", "i8ie_fc_u8", "i8ie_debug_tc_error",
     "i8ie_quantize_f32_u8_indirect", "i8ie_quantize_nchw_f32_nhwc_u8_indirect", "i8ie_copy_indirect",
     "i8ie_conv2d_f32_u8_indirect", "i8ie_top1_chunk_bytes", "i8ie_top1_pack", "i8ie_top1_unpack",
+    "i8ie_conv2d_f32", "i8ie_linear_f32", "i8ie_relu_f32", "i8ie_maxpool_f32_nchw",
 ]
 
 _lib = None
@@ -78,6 +79,10 @@ def load():
     L.i8ie_top1_pack.argtypes = [vp, vp, i, i, vp, vp]
     L.i8ie_top1_unpack.argtypes = [vp, i, i64, vp, vp, vp]
     L.i8ie_debug_tc_error.argtypes = [i]
+    L.i8ie_conv2d_f32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
+    L.i8ie_linear_f32.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp]
+    L.i8ie_relu_f32.argtypes = [vp, vp, i64, vp]
+    L.i8ie_maxpool_f32_nchw.argtypes = [vp, vp, i, i, i, i, i, i, vp]
     _lib = L
     return L
 

@@ -498,7 +498,7 @@ def dequantize(x):
 
 
 def relu(x):
-    """relu<T> — functional.cc:5-26. u8: max(x, zero_point) on device; fp32: torch glue."""
+    """relu<T> — functional.cc:5-26. u8: max(x, zero_point); fp32: max(x, 0)."""
     L = _need_cuda()
     if isinstance(x, TensorU8):
         pend = x._pending("layer")
@@ -508,7 +508,9 @@ def relu(x):
         check(L.i8ie_relu_u8(x.buf.data_ptr(), out.data_ptr(), x.buf.numel(), x._zp, _stream()), "relu_u8")
         return TensorU8(_Storage(out), x._shape, x._layout, x._geom, x._scale, x._zp)
     if isinstance(x, TensorF32):
-        return TensorF32(_Storage(torch.relu(x.buf)), x._shape)
+        out = torch.empty_like(x.buf)
+        check(L.i8ie_relu_f32(x.buf.data_ptr(), out.data_ptr(), x.buf.numel(), _stream()), "relu_f32")
+        return TensorF32(_Storage(out), x._shape)
     raise TypeError("relu(): unsupported tensor type")
 
 
@@ -527,8 +529,9 @@ def max_pool2d(x, kernel_size, strides):
         return TensorU8(None, [n, c, oh, ow], "nhwc", (n, c, oh, ow, cp), x._scale, x._zp,
                         deferred=_DeferredPool(x, k, s))
     if isinstance(x, TensorF32):
-        y = torch.nn.functional.max_pool2d(x.buf.view(n, c, h, w), k, s)
-        return TensorF32(_Storage(y.contiguous().reshape(-1)), [n, c, oh, ow])
+        y = torch.empty(n * c * oh * ow, dtype=torch.float32, device=x.buf.device)
+        check(L.i8ie_maxpool_f32_nchw(x.buf.data_ptr(), y.data_ptr(), n, c, h, w, k, s, _stream()), "maxpool_f32_nchw")
+        return TensorF32(_Storage(y), [n, c, oh, ow])
     raise TypeError("max_pool2d(): unsupported tensor type")
 
 
@@ -549,6 +552,23 @@ class Calibrator:
         self.mx = None
         self._ws = None
         self._out = None
+
+    def new_range(self, device):
+        """Device {min, max} pair a forward kernel folds its outputs into (fused calibrator pass)."""
+        return torch.tensor([np.finfo(np.float32).max, -np.finfo(np.float32).max], dtype=torch.float32, device=device)
+
+    def sample_range(self, t, mm):
+        """sample() for a layer output whose {min, max} the producing kernel already reduced."""
+        n = t.numel()
+        if n == 0:
+            return
+        if self.out_cnt < NUM_SAMPLES:
+            take = min(NUM_SAMPLES - self.out_cnt, n)
+            self.head.append(t.reshape(-1)[:take].cpu().numpy())
+        mn, mx = (float(v) for v in mm.cpu().numpy())
+        self.mn = mn if self.mn is None else min(self.mn, mn)
+        self.mx = mx if self.mx is None else max(self.mx, mx)
+        self.out_cnt += n
 
     def sample(self, t):
         L = _need_cuda()
@@ -707,18 +727,6 @@ class _BaseLayer:
         raise TypeError("__call__(): incompatible function arguments")
 
 
-class _tf32_off:
-    def __enter__(self):
-        self.a = torch.backends.cuda.matmul.allow_tf32
-        self.b = torch.backends.cudnn.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-        torch.backends.cudnn.allow_tf32 = False
-
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.a
-        torch.backends.cudnn.allow_tf32 = self.b
-
-
 class Linear(_BaseLayer):
     """Linear — include/fully_connected.h, src/fully_connected.cc."""
 
@@ -734,15 +742,21 @@ class Linear(_BaseLayer):
         self._w_packed = wp
 
     def _forward_f32(self, x):
-        # Linear::forward_prop(Tensor<float>&&), fully_connected.cc:5-21 — fp32 side is torch
-        # glue (TF32 off); it only feeds the calibrator.
+        # Linear::forward_prop(Tensor<float>&&), fully_connected.cc:5-21: fp32 FMA GEMM
+        # with the bias add and the calibrator's min/max (fully_connected.cc:17-19) in the epilogue
+        L = _lib.load()
         w, b = self._fp32_params()
-        m = x._shape[0]
-        with _tf32_off():
-            y = torch.nn.functional.linear(x.buf.view(m, -1), w, b).contiguous()
-        if self._is_preparing:
-            self._cal.sample(y)                       # fully_connected.cc:17-19
-        return TensorF32(_Storage(y.reshape(-1)), [m, w.shape[0]])
+        if len(x._shape) != 2 or x._shape[1] != w.shape[1]:
+            raise RuntimeError(f"Linear: input shape {tuple(x._shape)} does not match weight {tuple(w.shape)}")
+        m, k = x._shape
+        n = w.shape[0]
+        y = torch.empty(m * n, dtype=torch.float32, device=w.device)
+        mm = self._cal.new_range(w.device) if self._is_preparing else None
+        check(L.i8ie_linear_f32(x.buf.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), m, n, k,
+                                mm.data_ptr() if mm is not None else None, _stream()), "linear_f32")
+        if mm is not None:
+            self._cal.sample_range(y, mm)
+        return TensorF32(_Storage(y), [m, n])
 
     def _out_meta(self, x):
         if len(x._shape) != 2:
@@ -798,15 +812,26 @@ class Conv2d(_BaseLayer):
         return wp
 
     def _forward_f32(self, x):
-        # Conv2d::forward_prop(Tensor<float>&&), conv2d.cc:63-98 — torch glue, TF32 off
+        # Conv2d::forward_prop(Tensor<float>&&), conv2d.cc:63-98: fp32 implicit GEMM
+        # (no im2col buffer) with the bias add and the calibrator's min/max (conv2d.cc:94-96) fused
+        L = _lib.load()
         w, b = self._fp32_params()
+        if len(x._shape) != 4 or x._shape[1] != w.shape[1]:
+            raise RuntimeError(f"Conv2d: input shape {tuple(x._shape)} does not match weight {tuple(w.shape)}")
         n, c, h, wd = x._shape
-        with _tf32_off():
-            y = torch.nn.functional.conv2d(x.buf.view(n, c, h, wd), w, b, stride=self._stride,
-                                           padding=self._pad).contiguous()
-        if self._is_preparing:
-            self._cal.sample(y)                       # conv2d.cc:94-96
-        return TensorF32(_Storage(y.reshape(-1)), list(y.shape))
+        kc, _, kh, kw = w.shape
+        if h + 2 * self._pad < kh or wd + 2 * self._pad < kw:
+            raise RuntimeError("Conv2d: kernel larger than the padded input")
+        oh = (h - kh + 2 * self._pad) // self._stride + 1
+        ow = (wd - kw + 2 * self._pad) // self._stride + 1
+        y = torch.empty(n * kc * oh * ow, dtype=torch.float32, device=w.device)
+        mm = self._cal.new_range(w.device) if self._is_preparing else None
+        check(L.i8ie_conv2d_f32(x.buf.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, c, h, wd, kc, kh, kw,
+                                self._stride, self._pad, mm.data_ptr() if mm is not None else None, _stream()),
+              "conv2d_f32")
+        if mm is not None:
+            self._cal.sample_range(y, mm)
+        return TensorF32(_Storage(y), [n, kc, oh, ow])
 
     def _plan(self, n, c, h, w, cp, impl):
         key = (n, c, h, w, cp, impl)
