@@ -158,14 +158,16 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
     }
     if (p.fast_requant) {
       // exact requantise, two accumulators per packed fp32x2 instruction (see requant2_u8_fast);
-      // clamp + truncation are one saturating convert, relu is a max before it
+      // clamp + truncation are one saturating convert. relu<u8> = max(y, zp) (functional.cc:22-23)
+      // is applied to the ACCUMULATOR instead: with positive scales (requant_fast_ok) the requantised
+      // value is >= zp exactly when acc >= 0, and acc = 0 maps to zp itself, so max(acc, 0) gives the
+      // same byte — and fuses with the offset add above into one add-max instruction.
       if (p.ep.relu) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) requant2_u8_fast<true>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) requant2_u8_fast<false>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
+        for (int j = 0; j < 32; ++j) v[j] = (uint32_t)max((int32_t)v[j], 0);
       }
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) requant2_u8_fast<false>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
     } else {
       const uint32_t zlo = p.ep.relu ? (uint32_t)p.ep.zp_out : 0u;
 #pragma unroll

@@ -53,13 +53,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must never hang the GPU. Returns false on timeout
 // (~seconds), after which the caller records an error and bails out.
+// try_wait suspends the warp in hardware for a while before it reports failure, so a waiting warp
+// wakes up a few times per tile; the loop around it is kept to try_wait + count + branch (the clock
+// is only read every 64th wake-up) because those instructions compete with the working warps of
+// the same scheduler for issue slots.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) return false;
+  long long t0 = 0;
+  for (uint32_t n = 1;; ++n) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((n & 63u) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ll) return false;
+    }
   }
-  return true;
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {

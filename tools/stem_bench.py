@@ -35,6 +35,9 @@ def main():
     for x in xs:
         y = L.forward_quantize_fused(x, 0.025, 127)
     torch.cuda.synchronize()
+    if os.environ.get("I8IE_STEM2_TRACE"):   # eager launches only: the library dumps CTA 0's timeline
+        print("trace written to", os.environ["I8IE_STEM2_TRACE"])
+        return
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(args.reps):
