@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     # the requantise arithmetic must match the reference's IEEE fp32
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("I8IE_NVCC_EXTRA", "").split()
 
 
 def nvcc():

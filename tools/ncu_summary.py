@@ -46,32 +46,34 @@ def short(name: str) -> str:
 
 
 def launches(path: str) -> None:
-    rows = []
+    per = OrderedDict()   # launch ID -> {name, grid, block, ns, dram}
     with open(path, newline="") as f:
         lines = [ln for ln in f if ln.startswith('"')]
     for r in csv.DictReader(io.StringIO("".join(lines))):
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+        e = per.setdefault(r["ID"], {"name": short(r["Kernel Name"]), "grid": r["Grid Size"],
+                                     "block": r["Block Size"], "ns": 0.0, "dram": None})
         v = float(r["Metric Value"].replace(",", ""))
-        if r.get("Metric Unit") in ("us", "usecond"):
-            v *= 1e3
-        elif r.get("Metric Unit") in ("ms", "msecond"):
-            v *= 1e6
-        rows.append((short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], v))
-    total = sum(r[3] for r in rows)
+        u = (r.get("Metric Unit") or "").lower()
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            e["ns"] = v * {"us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}.get(u, 1)
+        elif r.get("Metric Name") in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            e["dram"] = (e["dram"] or 0.0) + v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+    rows = list(per.values())
+    total = sum(r["ns"] for r in rows)
     agg = OrderedDict()
-    for n, g, b, v in rows:
-        k = (n, g, b)
-        c = agg.setdefault(k, [0, 0.0])
+    for r in rows:
+        c = agg.setdefault((r["name"], r["grid"], r["block"]), [0, 0.0, 0.0, r["dram"] is not None])
         c[0] += 1
-        c[1] += v
+        c[1] += r["ns"]
+        c[2] += r["dram"] or 0.0
     print(f"# launch list summary: {path}")
     print(f"# {len(rows)} launches, {total / 1e3:.1f} us of GPU time "
-          "(ncu per-launch times are cold-cache and serialised: compare shares)")
-    print("| share % | launches | avg us | kernel | grid | block |")
-    print("|---|---|---|---|---|---|")
-    for (n, g, b), (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| {100 * v / total:5.1f} | {c} | {v / c / 1e3:8.2f} | `{n}` | {g} | {b} |")
+          "(ncu per-launch times are serialised, one kernel at a time: compare shares)")
+    print("| share % | launches | avg us | avg DRAM MB (rd+wr) | kernel | grid | block |")
+    print("|---|---|---|---|---|---|---|")
+    for (n, g, b), (c, v, d, has) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        dram = f"{d / c / 1e6:8.2f}" if has else "-"
+        print(f"| {100 * v / total:5.1f} | {c} | {v / c / 1e3:8.2f} | {dram} | `{n}` | {g} | {b} |")
 
 
 def report(path: str) -> None:
