@@ -189,8 +189,32 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: anything libraries print to fd 1 meanwhile (e.g. NCCL's
+    # version banner when the box sets NCCL_DEBUG) is sent to stderr; print_line() restores fd 1
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def print_line(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
+    verbose = os.environ.get("I8IE_BENCH_VERBOSE") is not None
+    t_start = time.time()
+
+    def stage(msg):
+        if verbose:
+            print(f"[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+    if verbose:   # a hung rank prints its Python stack to stderr
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("I8IE_BENCH_VERBOSE") or 90), exit=False, file=sys.stderr)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        stage("process group up")
 
     import i8ie
     from int8inferenceengine_b200 import _lib, backend as B, sharding
@@ -205,6 +229,7 @@ def run_ours(args):
     # model: weights seed 0 replicated on every rank, calibrated on one batch of 100 (seed 1)
     sd = W.make_weights(topo, 0)
     model = build_module(topo, sd, calib=W.make_images(topo, 100, 1))
+    stage("model built and calibrated")
 
     # inputs: a ring of distinct device-resident batches larger than L2 (126 MB) in total
     bytes_per_batch = lbatch * 3 * 224 * 224 * 4
@@ -246,8 +271,11 @@ def run_ours(args):
             ref_argmax.append(torch.cat(parts))
     del tsd
     torch.cuda.empty_cache()
+    stage("fp32 reference argmax done")
 
     # result exchange (N > 1): pack kernel -> ONE NCCL all-gather of [count | logits] -> unpack kernel
+    # (ResultExchange(overlap=True) would run gather + unpack on a side stream; measured on 8 B200s it
+    # changes nothing — 0.436 vs 0.429 ms per step — so the plain stream-ordered form is used)
     exchange = sharding.ResultExchange(gbatch, 10, torch.device("cuda", local)) if world > 1 else None
 
     def step(i):
@@ -264,7 +292,9 @@ def run_ours(args):
 
     for i in range(max(args.warmup, 3)):
         step(i)
+        stage(f"warm-up step {i} queued")
     sync_all()
+    stage("warm-up done")
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -283,11 +313,23 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     sampler.active = False
     ms = e0.elapsed_time(e1)
+    stage("timed region done")
     launches = _lib.launch_count() - launches0 + model.graph_launches() - glaunch0   # timed steps only
     clock_window = "timed region"
-    if len(sampler.samples) < 5 and not args.profiler_range:
-        # the timed region is only a few milliseconds (NVML answers in ~ms): keep sampling over
-        # ~0.5 s of the very same steps so that the clocks line describes the loaded state
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # the timed region is only a few milliseconds (NVML answers in ~ms): keep sampling over ~0.5 s of
+    # the very same steps so that the clocks line describes the loaded state. Every step holds a
+    # collective at N > 1, so whether and how many extra steps run is decided identically on all
+    # ranks (from the max-reduced time and an OR-reduced flag), never per rank.
+    need = 1 if (len(sampler.samples) < 5 and not args.profiler_range) else 0
+    if world > 1:
+        t = torch.tensor([need], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        need = int(t.item())
+    if need:
         extra = max(args.steps, int(0.5 / max(ms / args.steps * 1e-3, 1e-6)))
         sampler.active = True
         for i in range(extra):
@@ -295,10 +337,6 @@ def run_ours(args):
         sync_all()
         sampler.active = False
         clock_window = f"timed region + {extra} further identical steps (untimed, ~0.5 s)"
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_per_step = ms / args.steps
     value = gbatch / (ms_per_step * 1e-3)
     last = model(dev_inputs[0]).data.buf.view(lbatch, 10)
@@ -490,7 +528,7 @@ def run_ours(args):
             "hbm_kernels": hbm_rows,
             "hbm_peak_gbs": pk["hbm_gbs"],
         }
-        print(json.dumps(line))
+        print_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -61,7 +61,9 @@ class ResultExchange:
     that computed the count; handles uneven shards (each chunk carries its row count).
     CUDA only — the kernels live in libi8ie_sm100.so (include/i8ie_sm100.h, i8ie_top1_*)."""
 
-    def __init__(self, global_batch: int, cols: int, device):
+    def __init__(self, global_batch: int, cols: int, device, overlap: bool = False):
+        """overlap=True: the all-gather and the unpack run on a side stream (double-buffered chunks),
+        so the forward of the next step never waits for a peer; results are valid after `wait()`."""
         from . import _lib
         self._L = _lib.load()
         self._check = _lib.check
@@ -74,32 +76,57 @@ class ResultExchange:
         while (cap * cols) % 4:
             cap += 1
         self.chunk = int(self._L.i8ie_top1_chunk_bytes(cap, cols))
-        self.packed = torch.zeros(self.chunk, dtype=torch.uint8, device=device)
-        self.gathered = torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=device)
+        nbuf = 2 if overlap else 1
+        self._packed = [torch.zeros(self.chunk, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+        self._gathered = [torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+        self.packed, self.gathered = self._packed[0], self._gathered[0]
         self.logits_all = torch.empty(self.global_batch, cols, dtype=torch.float32, device=device)
         self.agree = torch.zeros(1, dtype=torch.int64, device=device)
+        self._side = torch.cuda.Stream(device=device) if overlap else None
+        self._done = [None] * nbuf     # side-stream events: chunk buffers free / results written
+        self._calls = 0
+
+    def wait(self):
+        """Make the current stream wait for every exchange issued so far (overlap mode)."""
+        for ev in self._done:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
 
     def __call__(self, local_logits: torch.Tensor, ref_argmax: torch.Tensor | None = None):
         """local_logits: [rows, cols] fp32 CUDA (contiguous); ref_argmax: [rows] int64 CUDA or None.
         Returns (logits of all ranks [global_batch, cols], agreement count tensor [1] int64) —
-        static buffers, valid until the next call; everything is stream-ordered, nothing syncs."""
+        static buffers, valid until the next call; everything is stream-ordered, nothing syncs
+        (overlap mode: valid once `wait()` has been called on the consuming stream)."""
         if not local_logits.is_cuda or local_logits.dtype != torch.float32 or not local_logits.is_contiguous():
             raise ValueError("ResultExchange needs a contiguous fp32 CUDA tensor")
         if tuple(local_logits.shape) != (self.rows, self.cols):
             raise ValueError(f"expected logits of shape {(self.rows, self.cols)}, got {tuple(local_logits.shape)}")
-        st = torch.cuda.current_stream().cuda_stream
+        cur = torch.cuda.current_stream()
         ref_ptr = None
         if ref_argmax is not None:
             if ref_argmax.dtype != torch.int64 or ref_argmax.numel() != self.rows or not ref_argmax.is_cuda:
                 raise ValueError("ref_argmax must be int64 CUDA with one entry per local row")
             ref_ptr = ref_argmax.data_ptr()
+        k = self._calls % len(self._packed)
+        self._calls += 1
+        packed, gathered = self._packed[k], self._gathered[k]
+        if self._done[k] is not None:      # the exchange that last used this chunk buffer has finished
+            cur.wait_event(self._done[k])
+        # pack on the caller's stream: it consumes the logits there (local work, no peer involved)
         self._check(self._L.i8ie_top1_pack(local_logits.data_ptr(), ref_ptr, self.rows, self.cols,
-                                           self.packed.data_ptr(), st), "top1_pack")
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.gathered, self.packed)
-            src = self.gathered
-        else:
-            src = self.packed
-        self._check(self._L.i8ie_top1_unpack(src.data_ptr(), self.world, self.chunk, self.logits_all.data_ptr(),
-                                             self.agree.data_ptr(), st), "top1_unpack")
+                                           packed.data_ptr(), cur.cuda_stream), "top1_pack")
+        run_on = cur
+        if self._side is not None:
+            self._side.wait_event(cur.record_event())
+            run_on = self._side
+        with torch.cuda.stream(run_on):
+            if self.world > 1:
+                dist.all_gather_into_tensor(gathered, packed)
+                src = gathered
+            else:
+                src = packed
+            self._check(self._L.i8ie_top1_unpack(src.data_ptr(), self.world, self.chunk, self.logits_all.data_ptr(),
+                                                 self.agree.data_ptr(), run_on.cuda_stream), "top1_unpack")
+            if self._side is not None:
+                self._done[k] = run_on.record_event()
         return self.logits_all, self.agree
