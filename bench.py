@@ -120,10 +120,20 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every worker; the reference arm is ONE process that is
+    # meant to use all host cores (its conv loop is `omp parallel for` over images, conv2d.cc:125)
+    if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    threads = int(os.environ["OMP_NUM_THREADS"])
     topo = "alexnet"
     batch = args.batch or (100 if args.gpus == 1 else 1000)
     model, kind = ref_model_and_qparams(topo)
+    try:   # an OpenMP runtime that was initialised before the variable changed
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(threads)
+    except Exception:  # noqa: BLE001
+        pass
     # bounded sample: size the per-step sample so (steps + warmup) steps end within ~2.5 minutes
     probe = W.make_images(topo, 4, 2)
     model.forward_int8(probe)
