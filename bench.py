@@ -80,7 +80,9 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            # 10 ms: ~50 samples over the 0.5 s loaded window; a faster poll only competes with the launch
+            # loop for the GIL and, at N ranks, N pollers queue on the driver's NVML lock
+            time.sleep(0.010)
 
     def stop(self):
         self._stop_evt.set()
