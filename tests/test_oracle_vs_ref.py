@@ -59,3 +59,48 @@ def test_random_conv_geometries():
         got = port.conv2d_u8(np.array(q.numpy()), qw, qb, s, p, np.float32(0.03), zp, ws,
                              np.float32(o.scale()), int(o.zero_point()))
         assert np.array_equal(got, np.array(o.numpy())), (c, kc, k, s, p, h, w_)
+
+
+def test_random_linear_geometries():
+    # Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52, incl. 1-row / 1-feature shapes,
+    # zero points at both ends of the range and inputs that saturate the requantise clamp
+    m = ref.module()
+    rng = np.random.default_rng(11)
+    for it in range(12):
+        rows, k, n = int(rng.integers(1, 40)), int(rng.integers(1, 300)), int(rng.integers(1, 70))
+        wt = rng.uniform(-0.4, 0.4, size=(n, k)).astype(np.float32)
+        b = rng.uniform(-0.2, 0.2, size=(n,)).astype(np.float32)
+        x = rng.uniform(-4, 4, size=(max(rows, 100), k)).astype(np.float32)   # >= 1000 outputs: see SURVEY A9
+        L = m.Linear(k, n)
+        L.load_weight(wt)
+        L.load_bias(b)
+        L.prepare()
+        L(m.tensor(x))
+        L.convert()
+        zp = int((0, 255, 127)[it % 3] if it < 6 else rng.integers(0, 256))
+        q = m.quantize(m.tensor(x[:rows]), 0.04, zp)
+        o = L(q)
+        qw, qb, ws = port.quantize_weight(wt, b)
+        got = port.linear_u8(np.array(q.numpy()), qw, qb, np.float32(0.04), zp, ws,
+                             np.float32(o.scale()), int(o.zero_point()))
+        assert np.array_equal(got, np.array(o.numpy())), (rows, k, n, zp)
+
+
+def test_random_elementwise_and_pool():
+    # quantize (unclamped, wrapping: quantize_utils.cc:44-52), dequantize (:54-58), relu<u8>
+    # (functional.cc:15-26) and max_pool2d<u8> (:36-64) incl. overlapping / ragged windows
+    m = ref.module()
+    rng = np.random.default_rng(12)
+    for _ in range(10):
+        n, c = int(rng.integers(1, 4)), int(rng.integers(1, 7))
+        h, w_ = int(rng.integers(3, 20)), int(rng.integers(3, 20))
+        x = rng.uniform(-9, 9, size=(n, c, h, w_)).astype(np.float32)   # beyond the 0.025/127 window: wraps
+        scale, zp = np.float32(rng.choice([0.025, 0.05, 0.1])), int(rng.integers(0, 256))
+        q = m.quantize(m.tensor(x), float(scale), zp)
+        qn = np.array(q.numpy())
+        assert np.array_equal(port.quantize(x, scale, zp), qn)
+        assert np.array_equal(port.dequantize(qn, scale, zp), np.array(m.dequantize(q).numpy()))
+        assert np.array_equal(port.relu_u8(qn, zp), np.array(m.relu(q).numpy()))
+        k = int(rng.integers(1, min(h, w_, 4) + 1))
+        s = int(rng.integers(1, 4))
+        assert np.array_equal(port.max_pool2d_u8(qn, k, s), np.array(m.max_pool2d(q, k, s).numpy())), (h, w_, k, s)
