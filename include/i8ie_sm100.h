@@ -89,6 +89,33 @@ I8IE_API int i8ie_top1_pack(const float* logits, const int64_t* ref_argmax, int 
 I8IE_API int i8ie_top1_unpack(const void* gathered, int world, int64_t chunk_bytes, float* logits_all,
                      int64_t* agree_total, void* stream);
 
+/* ---- the same exchange over NVLink / NVSwitch PEER MEMORY (csrc/peer_exchange.cu) --------------
+ * No NCCL call and no host involvement per step, so forward + exchange replay as ONE CUDA graph.
+ * Every rank owns one shareable buffer of i8ie_peer_exchange_bytes(world, chunk) bytes
+ *   [ flags: 16 x u64 | gathered[2][world][chunk] ]        (zero-initialised by i8ie_peer_alloc)
+ * created with i8ie_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; handle64 = the 64-byte IPC handle
+ * to hand to the peers, e.g. through torch.distributed.all_gather_object) and mapped by every peer
+ * with i8ie_peer_open. peer_bases[p] = rank p's buffer as mapped in the calling process (own
+ * buffer: the pointer i8ie_peer_alloc returned).
+ *   i8ie_top1_pack_push   packs this rank's chunk (as i8ie_top1_pack) straight into slot `rank` of
+ *                         gathered[seq & 1] on EVERY rank with peer stores, then publishes seq in word
+ *                         `rank` of every rank's flags (st.release.sys). seq = ++*seq_counter, a u64
+ *                         in local device memory (initially 0), so a graph replay needs no argument.
+ *   i8ie_top1_wait_unpack waits (bounded, ~15 s) until all `world` flag words of the local buffer
+ *                         reached *seq_counter, then unpacks gathered[seq & 1] as i8ie_top1_unpack does.
+ *                         A timeout is reported through i8ie_tc_error_poll (code 7).
+ * One rank per GPU; all ranks must call the pair once per step, in the same order. */
+I8IE_API int64_t i8ie_peer_exchange_bytes(int world, int64_t chunk_bytes);
+I8IE_API int i8ie_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+I8IE_API int i8ie_peer_open(const void* handle64, void** ptr);
+I8IE_API int i8ie_peer_close(void* ptr);
+I8IE_API int i8ie_peer_free(void* ptr);
+I8IE_API int i8ie_top1_pack_push(const float* logits, const int64_t* ref_argmax, int rows, int cols,
+                                 void* const* peer_bases, int world, int rank, int64_t chunk_bytes,
+                                 void* seq_counter, void* stream);
+I8IE_API int i8ie_top1_wait_unpack(const void* mine, int world, int64_t chunk_bytes, const void* seq_counter,
+                                   float* logits_all, int64_t* agree_total, void* stream);
+
 /* ---- F1: the FP32 forward (calibration side; feeds Calibrator::sample) -------------------------
  * Conv2d::forward_prop(Tensor<float>&&), conv2d.cc:63-98: im2col + cblas_sgemm + bias, here one
  * implicit-GEMM fp32 FMA kernel. x dense NCHW [n,c,h,w], w OIHW [kc,c,kh,kw], bias [kc],
@@ -215,6 +242,12 @@ I8IE_API int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int
  * returns the first protocol error (mbarrier wait timeout) a tensor-core kernel recorded
  * (0 = none, >0 = role that timed out), optionally clearing it; negative on CUDA errors. */
 I8IE_API int i8ie_debug_tc_error(int reset);
+
+/* Same flag, read from a host-mapped mirror WITHOUT any CUDA call or synchronisation: valid once
+ * the work in question has been synchronised by the caller (e.g. right after a device-to-host
+ * copy of a result). The Python layer checks it on every result read-back and raises, so a
+ * pipeline fault can never return garbage activations with rc = 0. */
+I8IE_API int i8ie_tc_error_poll(int reset);
 
 #ifdef __cplusplus
 }

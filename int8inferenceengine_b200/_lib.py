@@ -20,6 +20,8 @@ SYMBOLS = [
     "i8ie_quantize_f32_u8_indirect", "i8ie_quantize_nchw_f32_nhwc_u8_indirect", "i8ie_copy_indirect",
     "i8ie_conv2d_f32_u8_indirect", "i8ie_top1_chunk_bytes", "i8ie_top1_pack", "i8ie_top1_unpack",
     "i8ie_conv2d_f32", "i8ie_linear_f32", "i8ie_relu_f32", "i8ie_maxpool_f32_nchw",
+    "i8ie_tc_error_poll", "i8ie_peer_exchange_bytes", "i8ie_peer_alloc", "i8ie_peer_open", "i8ie_peer_close",
+    "i8ie_peer_free", "i8ie_top1_pack_push", "i8ie_top1_wait_unpack",
 ]
 
 _lib = None
@@ -79,6 +81,15 @@ def load():
     L.i8ie_top1_pack.argtypes = [vp, vp, i, i, vp, vp]
     L.i8ie_top1_unpack.argtypes = [vp, i, i64, vp, vp, vp]
     L.i8ie_debug_tc_error.argtypes = [i]
+    L.i8ie_tc_error_poll.argtypes = [i]
+    L.i8ie_peer_exchange_bytes.argtypes = [i, i64]
+    L.i8ie_peer_exchange_bytes.restype = i64
+    L.i8ie_peer_alloc.argtypes = [i64, C.POINTER(vp), vp]
+    L.i8ie_peer_open.argtypes = [vp, C.POINTER(vp)]
+    L.i8ie_peer_close.argtypes = [vp]
+    L.i8ie_peer_free.argtypes = [vp]
+    L.i8ie_top1_pack_push.argtypes = [vp, vp, i, i, C.POINTER(vp), i, i, i64, vp, vp]
+    L.i8ie_top1_wait_unpack.argtypes = [vp, i, i64, vp, vp, vp, vp]
     L.i8ie_conv2d_f32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
     L.i8ie_linear_f32.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp]
     L.i8ie_relu_f32.argtypes = [vp, vp, i64, vp]
@@ -94,6 +105,23 @@ def last_error():
 def check(rc, what=""):
     if rc != 0:
         raise I8ieError(f"{what or 'i8ie call'} failed (code {rc}): {last_error()}")
+
+
+_TC_ROLES = {1: "TMA producer waiting for a free operand stage", 2: "MMA issuer waiting for operands",
+             3: "epilogue waiting for an accumulator", 4: "MMA issuer waiting for a drained accumulator",
+             5: "stem MMA issuer waiting for the weights", 6: "stem converter waiting for fp32 rows",
+             7: "result exchange waiting for a peer rank's chunk"}
+
+
+def check_tc_error():
+    """Raises if a tensor-core kernel recorded a pipeline fault (mbarrier wait timeout) on the
+    current device. Reads a host-mapped flag (no CUDA call); call after a synchronisation."""
+    if _lib is None:
+        return
+    code = int(_lib.i8ie_tc_error_poll(1))
+    if code != 0:
+        raise I8ieError(f"a kernel hit a bounded-wait timeout (role {code}: "
+                        f"{_TC_ROLES.get(code, 'unknown')}); its output is invalid")
 
 
 def launch_count():

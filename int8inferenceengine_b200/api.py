@@ -122,7 +122,11 @@ class Module:
 
     # Extension (not in the reference): after two eager calls with the same input shape the
     # quantised forward is captured into a CUDA graph and replayed (the reference runs one op
-    # at a time under the GIL). Results are identical; set `graph = False` to opt out.
+    # at a time under the GIL). Results are identical as long as forward() is a pure function of
+    # its input and the layers' state: the cache is keyed on (shape, device, backend.graph_epoch()),
+    # and the epoch moves whenever a layer's (scale, zero_point), weights or fuse_relu change, so a
+    # stale graph is never replayed. A forward() with Python-side state or data-dependent control
+    # flow must set `graph = False`.
     graph = True
 
     def __call__(self, x):
@@ -160,7 +164,9 @@ class Module:
 
     def _call_graphed(self, x):
         cache = self.__dict__.setdefault("_graphs", {})
-        key = tuple(x.data.shape)
+        key = (tuple(x.data.shape), x.data.buf.device.index, _B.graph_epoch())
+        if cache and next(iter(cache))[2] != key[2]:
+            cache.clear()                            # graphs of an older epoch have stale parameters baked in
         st = cache.setdefault(key, {"calls": 0, "graph": None})
         if st["graph"] is None:
             st["calls"] += 1
@@ -168,6 +174,8 @@ class Module:
                 return self._call_eager(x)          # warm-up: builds plans, offsets, packed weights
             try:
                 st.update(_B.capture_forward(self._call_eager, x.data))
+                # the graph holds raw pointers into the layers' plans and packed weights
+                st["keep"] = [v for v in self.__dict__.values() if issubclass(type(v), Layer)]
             except Exception as e:  # noqa: BLE001 - e.g. a forward() that leaves the engine mid-way
                 import warnings
                 warnings.warn(f"i8ie: CUDA-graph capture of {type(self).__name__}.forward failed ({e}); "

@@ -30,6 +30,18 @@ from . import _lib
 from ._lib import I8ieError, check
 
 NUM_SAMPLES = 1000  # include/calibrator.h:4
+
+# Bumped whenever something a captured CUDA graph has baked in changes (a layer's (scale, zero_point),
+# its weights, its fuse_relu flag): api.Module keys its graph cache on it, so a stale graph is never replayed.
+_GRAPH_EPOCH = [0]
+
+
+def graph_epoch():
+    return _GRAPH_EPOCH[0]
+
+
+def _bump_epoch():
+    _GRAPH_EPOCH[0] += 1
 _F32_MAX_EXACT = 1 << 24
 
 
@@ -176,6 +188,19 @@ def pending_chunks(x):
     return [(TensorF32(_Storage(st._t[a * per:b * per]), [b - a] + x._shape[1:]), ev) for a, b, ev in st.chunks]
 
 
+def host_buffer_free(x):
+    """Blocks until the asynchronous host->device copy behind a tensor made from a pinned CPU
+    tensor has finished, i.e. until the caller may overwrite that pinned buffer."""
+    st = x._storage
+    if isinstance(st, _ChunkedStorage):
+        if st.chunks:
+            st.chunks[-1][2].synchronize()
+        else:
+            torch.cuda.current_stream().synchronize()
+    elif st is not None:
+        torch.cuda.current_stream().synchronize()
+
+
 def wait_event(ev):
     torch.cuda.current_stream().wait_event(ev)
 
@@ -234,7 +259,9 @@ class _TensorBase:
         return self._st.views
 
     def numpy(self):
-        return self._dense_buf().view(self._shape).cpu().numpy()
+        out = self._dense_buf().view(self._shape).cpu().numpy()
+        _lib.check_tc_error()     # the D2H copy synchronised: a pipeline fault upstream raises here
+        return out
 
     def sum(self):
         # pybind11.cc:18-25: sequential fp32 running sum
@@ -433,7 +460,13 @@ def _new_u8_nhwc(buf, n, c, h, w, cp, scale, zp, two_d=False):
 
 def tensor(ndarray):
     """_CXX_i8ie.tensor: py::array_t<float> force-casts anything array-like to f32 and copies
-    it in (tensor.h:40-47)."""
+    it in (tensor.h:40-47).
+
+    numpy arrays and pageable CPU tensors are copied synchronously, like the reference. A PINNED
+    CPU torch tensor is the fast path: its host->device copy is asynchronous (row chunks on a side
+    stream, see _ChunkedStorage) and no host-side copy is made, so the caller must not overwrite
+    the pinned buffer until the copy has finished — call `host_buffer_free(t)` (blocks until the
+    last chunk has left the host buffer) before reusing it, or pass a numpy array instead."""
     _need_cuda()
     if isinstance(ndarray, torch.Tensor) and ndarray.device.type == "cpu":
         # same force-cast; a pinned f32 tensor goes to the device without a staging copy
@@ -626,19 +659,31 @@ class _BaseLayer:
         self._w_packed = None           # s8, kernel layout
         self._oc_cache = {}
         self._plans = {}
-        self.fuse_relu = False          # extension: fold a following relu<u8> into the epilogue
+        self._fuse_relu = False         # extension: fold a following relu<u8> into the epilogue
+
+    @property
+    def fuse_relu(self):
+        return self._fuse_relu
+
+    @fuse_relu.setter
+    def fuse_relu(self, v):
+        if bool(v) != self._fuse_relu:
+            _bump_epoch()
+        self._fuse_relu = bool(v)
 
     def load_weight(self, w):
         if self._w is None:
             raise RuntimeError("std::exception")      # layer.h:16-18
         self._w = np.ascontiguousarray(np.asarray(w), dtype=np.float32)
         self._w_dev = None
+        _bump_epoch()
 
     def load_bias(self, b):
         if self._w is None:
             raise RuntimeError("std::exception")      # layer.h:22-24
         self._b = np.ascontiguousarray(np.asarray(b), dtype=np.float32)
         self._b_dev = None
+        _bump_epoch()
 
     def prepare(self):
         if self._is_quantized:
@@ -656,6 +701,8 @@ class _BaseLayer:
         self._cal = None
         self._is_preparing = False
         self._injected = True
+        self._oc_cache = {}
+        _bump_epoch()
 
     def convert(self):
         L = _need_cuda()
@@ -680,6 +727,7 @@ class _BaseLayer:
         self._pack()
         self._is_preparing = False
         self._is_quantized = True
+        _bump_epoch()
         self._w = None          # layer.cc:52-53 frees the fp32 parameters
         self._b = None
         self._w_dev = None

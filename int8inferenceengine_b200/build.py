@@ -57,8 +57,11 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libi8ie_sm100.so")
+    # libcudart is linked SHARED: the process already holds one (torch's), and a statically linked
+    # runtime would embed a second copy of it in the shipped artefact. The rpath covers a process
+    # that loads the library before torch (tests/test_abi.py on a CPU box).
     link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
-            "-Xcompiler", "-fPIC", "-cudart", "static"]
+            "-Xcompiler", "-fPIC", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

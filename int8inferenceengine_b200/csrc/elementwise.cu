@@ -8,6 +8,8 @@
 
 #include "common.cuh"
 
+namespace i8ie { int tc_error_sink_init(); }   // tc_gemm.cu
+
 namespace i8ie {
 
 thread_local char g_err[512] = "";
@@ -668,7 +670,7 @@ int i8ie_device_check(void) {
     set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
     return I8IE_ENOTSM100;
   }
-  return I8IE_OK;
+  return i8ie::tc_error_sink_init();   // host-mapped mirror of the tensor-core kernels' protocol-error flag
 }
 
 static int quantize_flat(const float* x, const float* const* xslot, uint8_t* q, int64_t n, float scale, int zp,

@@ -92,6 +92,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
     set_error("conv2d_plan_create: kernel larger than padded input");
     return nullptr;
   }
+  tc_error_sink_init();   // plans are created eagerly (never under stream capture)
   i8ie_conv_plan* p = new (std::nothrow) i8ie_conv_plan();
   if (!p) { set_error("conv2d_plan_create: out of host memory"); return nullptr; }
   GemmGeom& g = p->g;
@@ -149,7 +150,6 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
     p->bk = tc_conv_bk(g);
     p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
     p->cluster = tc_conv_cluster(p->bk, p->bn);
-    if (p->cluster == 2 && tc_conv_strip_eligible(g, p->bk, p->bn)) p->cluster = 4;   // pair kernel with A strips
     rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->cluster > 1 ? p->bn / 2 : p->bn);
     const int tab = tc_border_table_size(g);
     if (rc == I8IE_OK && tab > 0) {
@@ -181,6 +181,7 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   I8IE_REQUIRE(plan && x && y && oc, "conv2d_u8: null argument");
   I8IE_REQUIRE(zp_in >= 0 && zp_in <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_u8: zero point out of range");
   EpiParams ep{oc, nullptr, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  tc_error_sink_touch((cudaStream_t)stream);
   if (plan->impl == 3) {
     int rc = tc_stem_pack_input(plan->g, plan->stem, x, plan->stem_x, zp_in, (cudaStream_t)stream);
     if (rc != I8IE_OK) return rc;
@@ -190,9 +191,8 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   }
   if (plan->impl == 2) {
     CUtensorMap tmA;
-    int rc = plan->amaps.get(x, plan->cluster == 4, 0, 0, 0, &tmA, [&](CUtensorMap* m) {
-      return plan->cluster == 4 ? tc_encode_act_map_strip(m, x, plan->g) : tc_encode_act_map_im2col(m, x, plan->g, plan->bk);
-    });
+    int rc = plan->amaps.get(x, 0, 0, 0, 0, &tmA,
+                             [&](CUtensorMap* m) { return tc_encode_act_map_im2col(m, x, plan->g, plan->bk); });
     if (rc != I8IE_OK) return rc;
     return launch_tc_conv(plan->g, tmA, plan->tmB, plan->bk, plan->bn, plan->cluster, plan->border_tab, y, ep, zp_in,
                           (cudaStream_t)stream);
@@ -207,6 +207,7 @@ static int conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, const float*
   I8IE_REQUIRE(plan->impl == 3, "conv2d_f32_u8: only stem plans fuse the input quantise (plan impl=%d)", plan->impl);
   I8IE_REQUIRE(in_zp >= 0 && in_zp <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_f32_u8: zero point out of range");
   EpiParams ep{oc, nullptr, in_scale, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  tc_error_sink_touch((cudaStream_t)stream);
   if (plan->stem2 && tc_stem2_can_fuse_quantize(plan->g, plan->c, x_nchw, x_slot, in_scale)) {
     // the stem kernel's producer warps quantise the fp32 image straight into its operand ring
     const StemF32Src src{x_nchw, x_slot, in_scale, in_zp};
@@ -243,6 +244,7 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
                "fc_u8: bad shape/pitch (m=%d n=%d k=%d ldx=%d ldw=%d ldy=%d n_pad=%d)", m, n, k, ldx, ldw, ldy, n_pad);
   I8IE_REQUIRE(zp_out >= 0 && zp_out <= 255, "fc_u8: zero point out of range");
   EpiParams ep{oc, bias_f, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  tc_error_sink_touch((cudaStream_t)stream);
   // shape dispatch: the tensor-core kernel needs at least one full 32-byte K step to be worthwhile
   const bool eligible = !tc_disabled() && k >= 32;
   I8IE_REQUIRE(!(impl == 2 && !eligible), "fc_u8: shape not eligible for the tcgen05 kernel");
@@ -279,5 +281,10 @@ int i8ie_debug_tc_error(int reset) {
   int rc = tc_read_error(&v, reset != 0);
   return rc != I8IE_OK ? rc : v;
 }
+
+// Non-synchronising check used by the product paths (numpy(), dequantise read-back, bench, smoke):
+// first protocol error mirrored into host-mapped memory on the current device (0 = none).
+// Meaningful once the work in question has been synchronised (e.g. right after a D2H copy).
+int i8ie_tc_error_poll(int reset) { return tc_error_poll(reset != 0); }
 
 }  // extern "C"

@@ -36,15 +36,16 @@ int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* ta
 int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn);
 int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int bk);
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx);
-bool tc_conv_strip_eligible(const GemmGeom& g, int bk, int bn);   // stride-1 A-strip variant of the pair kernel
-int tc_encode_act_map_strip(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g);
-int tc_conv_cluster(int bk, int bn);   // CTAs per cluster sharing one multicast weight tile (1 or 2)
+int tc_conv_cluster(int bk, int bn);   // 2 = CTA-pair kernel (cta_group::2), 1 = single CTAs
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream);
 void tc_fc_config(int m, int ldy, int k, int* bn, int* splits, int* kb_per);
 int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
                  int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream);
 int tc_read_error(int* out, bool reset);
+int tc_error_sink_init();         // host-mapped mirror of the protocol-error flag (call outside stream capture)
+void tc_error_sink_touch(cudaStream_t stream);   // launch paths: lazily creates the sink unless capturing
+int tc_error_poll(bool reset);    // reads the mirror: no CUDA call, valid after a synchronisation
 
 // stem path (small-C strided first-layer convs), see tc_gemm.cu
 struct StemGeom {

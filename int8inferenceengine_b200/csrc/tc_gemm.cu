@@ -30,6 +30,23 @@
 namespace i8ie {
 
 __device__ int g_tc_error = 0;  // first protocol error seen by any tensor-core kernel (0 = none)
+// Host-mapped mirror of g_tc_error (pinned, zero-copy): the host reads it after any synchronising
+// call (numpy(), the end of a timed region, smoke()) WITHOUT another CUDA call, so a barrier timeout
+// surfaces as an exception at the next result read instead of as silently wrong activations.
+__device__ int* g_tc_error_host = nullptr;
+
+// A bounded mbarrier wait expired (see ptx::mbar_wait): record the role that timed out.
+//   1 producer waiting for a free operand stage   2 MMA issuer waiting for operands
+//   3 epilogue waiting for an accumulator         4 MMA issuer waiting for a drained accumulator
+//   5 stem MMA issuer waiting for the weights     6 stem converter waiting for fp32 rows
+__device__ __noinline__ void tc_fail(int code) {
+  atomicCAS(&g_tc_error, 0, code);
+  int* h = g_tc_error_host;
+  if (h != nullptr) {
+    *reinterpret_cast<volatile int*>(h) = code;
+    __threadfence_system();
+  }
+}
 
 struct TcParams {
   int M, N, out_cp;
@@ -51,13 +68,8 @@ struct TcParams {
   // 128-row sub-tiles per CTA tile (1 or 2): two accumulators share every weight stage, which
   // cuts the L2->SM bytes per MAC (the binding limit of a 128 x BN tile, ~43 B/clk/SM)
   int mt;
-  // thread-block cluster of `cluster` CTAs (1 or 2) along M: the CTAs of a cluster work on adjacent
-  // M tiles of the SAME N tile, each loads 1/cluster of the weight tile and TMA-multicasts it to all
-  // of them — the weight stream is the larger share of the L2->SM traffic this kernel is bound by
-  int cluster, tiles_mp;   // tiles_mp = ceil(tiles_m / cluster)
-  // strip kernel (tc_igemm2s_kernel): output positions are enumerated over the PADDED width
-  // owp = W + 2*pad (the last kw-1 positions of a row are computed but never stored), Mp = n*oh*owp
-  int owp, Mp, stages_a;
+  // CTA-pair kernel: tiles_mp = ceil(tiles_m / 2) 256-row pair tiles; single-CTA kernel: tiles_mp = tiles_m
+  int tiles_mp;
 };
 
 namespace {
@@ -207,19 +219,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cl = p.cluster;                               // cluster dims are (cl, 1, 1)
-  const int crank = cl > 1 ? (int)(blockIdx.x % cl) : 0;  // == %cluster_ctarank
-  const int mn_tiles = p.tiles_mp * p.tiles_n;            // tiles of a whole cluster (cl adjacent M tiles each)
+  const int mn_tiles = p.tiles_m * p.tiles_n;
   const int num_tiles = mn_tiles * p.splits;
-  const int tile0 = blockIdx.x / cl, tile_step = gridDim.x / cl;
-  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+  const int tile0 = blockIdx.x, tile_step = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
-      ptx::mbar_init(&ctl->empty[s], cl);   // every CTA that reads the multicast weight tile releases it
+      ptx::mbar_init(&ctl->empty[s], 1);
     }
     for (int b = 0; b < (int)NACC; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
@@ -232,7 +241,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
-  if (cl > 1) ptx::cluster_sync_all();   // peers' barriers are initialised before anything is multicast to them
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
@@ -242,9 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
       bool alive = true;
       for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
         const int split = tile / mn_tiles, mn = tile % mn_tiles;
-        // a cluster's tail tile beyond the last M tile re-loads the last one (its stores are masked)
-        const int mtile = min((mn / p.tiles_n) * cl + crank, p.tiles_m - 1);
-        const int m0 = mtile * BM * mt, n0 = (mn % p.tiles_n) * BN;
+        const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
         int bw[MT] = {}, bh[MT] = {}, bn[MT] = {};
         if (MODE == 1) {
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
           ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)kStage);
           uint8_t* sa = smem + (size_t)s * kStage;
           uint8_t* sb = sa + p.ksub * mt * kSubA;
@@ -276,11 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                 ptx::tma_load_2d(dst, &tmA, &ctl->full[s], kidx * BK, m0 + t * BM);
             }
             if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } } }
-            if (cl > 1)   // my 1/cl of the weight rows, delivered to every CTA of the cluster
-              ptx::tma_load_2d_multicast(sb + j * kSubB + crank * (kSubB / cl), &tmB, &ctl->full[s], kidx * BK,
-                                         n0 + crank * (BN / cl), cmask);
-            else
-              ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
+            ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
           }
         }
       }
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
 #pragma unroll
         for (int t = 0; t < mt; ++t) {
           const uint32_t slot = (acc_it + t) % NACC, sph = ((acc_it + t) / NACC) & 1;
-          if (alive && !ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; }
+          if (alive && !ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { tc_fail(4); alive = false; }
           d_tmem[t] = tmem_base + slot * acc_stride<BN>();
         }
         if (!alive) break;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+          if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
           // descriptor low words; every further operand is a constant (>>4) offset away
@@ -325,10 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             a_lo += (uint32_t)((mt * kSubA) >> 4);
             b_lo += (uint32_t)(kSubB >> 4);
           }
-          // slot reusable once these MMAs have read it; with a cluster every CTA's slot also holds
-          // weight rows multicast by the peers, so the release goes to all of them
-          if (cl > 1) ptx::tc_commit_multicast(&ctl->empty[s], cmask);
-          else ptx::tc_commit(&ctl->empty[s]);
+          ptx::tc_commit(&ctl->empty[s]);   // slot reusable once these MMAs have read it
         }
         if (alive) {
 #pragma unroll
@@ -348,9 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount, acc_it += mt) {
       const uint32_t ob = tcount & 1;
       const int split = tile / mn_tiles, mn = tile % mn_tiles;
-      const int mtile = (mn / p.tiles_n) * cl + crank;
-      const bool tile_valid = mtile < p.tiles_m;          // false: a cluster's tail tile past the last M tile
-      const int m0 = min(mtile, p.tiles_m - 1) * BM * mt, n0 = (mn % p.tiles_n) * BN;
+      const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
       if (p.splits <= 1) {
         // stage this tile's per-channel offsets (double-buffered: one barrier per tile)
         for (int j = et; j < BN; j += 32 * kEpiWarps) {
@@ -368,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         if (p.splits > 1) {
           // split-K: dump the raw partial accumulators; fc_splitk_reduce_kernel finishes the job
           const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
-          if (!ok) atomicCAS(&g_tc_error, 0, 3);
+          if (!ok) tc_fail(3);
           ptx::tc_fence_after();
           int32_t* wrow = p.ws + ((size_t)split * p.M + (m < p.M ? m : 0)) * p.ws_ld + n0;
 #pragma unroll 1
@@ -376,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
-            if (m < p.M && ok && tile_valid) {
+            if (m < p.M && ok) {
 #pragma unroll
               for (int g = 0; g < 8; ++g)
                 *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -395,9 +392,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
           }
           const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
-          if (!ok) atomicCAS(&g_tc_error, 0, 3);
+          if (!ok) tc_fail(3);
           ptx::tc_fence_after();
-          epilogue_row<BN>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
+          epilogue_row<BN>(p, t_row, (m < p.M && ok) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
                            ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
         }
         // hand the accumulator buffer back to the MMA warp
@@ -409,7 +406,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (cl > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer may still multicast to it or arrive on its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
 }
 
@@ -477,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
           if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], 2u * (uint32_t)kStage);
           uint8_t* sa = smem + (size_t)s * kStage;
           ptx::tma_load_im2col_4d_2cta(sa, &tmA, &ctl->full[s], cb * BK, bw, bh, bimg, (uint16_t)kx, (uint16_t)ky);
@@ -495,14 +491,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
       bool alive = true;
       for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step, ++acc_it) {
         const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
-        if (!ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
+        if (!ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { tc_fail(4); alive = false; break; }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + slot * acc_stride<BN>();
         uint32_t accf = 0;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+          if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
           const uint32_t a_lo = ptx::smem_desc_lo(sa), b_lo = ptx::smem_desc_lo(sa + kSubA);
@@ -550,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
         if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
       }
       const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
-      if (!ok) atomicCAS(&g_tc_error, 0, 3);
+      if (!ok) tc_fail(3);
       ptx::tc_fence_after();
       epilogue_row<BN>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
                        ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
@@ -566,204 +562,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();   // no CTA leaves while its peer may still use its shared memory, barriers or TMEM
-  if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols<BN>());
-}
-
-// ---- CTA-pair kernel with A strips (stride-1 convs) -----------------------------------------------
-// im2col fetches every input pixel once per filter tap. For stride 1 the kw taps of one filter row
-// read the SAME pixels shifted by one: if output positions are enumerated over the padded width
-// (owp = W + 2*pad positions per row, the last kw-1 are garbage and never stored), tap kx of output
-// position m is row m + kx of ONE strip of 128 + kw - 1 consecutive positions at tap 0. So the
-// producer loads one strip per (filter row, channel block) and the MMA walks the kw taps by moving
-// the A descriptor's start address one 128-byte row at a time. A ingest per K block falls from
-// 16 KB to 16.5 KB / kw. Two rings: weight K blocks (full/empty, as before) and A strips
-// (a_full/a_empty). Bit-exact, but measured SLOWER than the plain pair kernel (the 15 % extra
-// positions cost more than the saved ingest buys), so it is opt-in (I8IE_STRIP=1) — kept as the
-// starting point for physically padded activations, where the extra positions disappear.
-constexpr int kStripRows = 136;                 // 128 + (kw - 1) <= 136 -> kw <= 9
-constexpr int kStripBytes = kStripRows * 128;   // 17 x 1 KB swizzle atoms
-constexpr int kMaxStagesA = 4;
-
-template <int BN>
-struct alignas(16) TcControlS {
-  TcControl<BN> c;
-  uint64_t a_full[kMaxStagesA];
-  uint64_t a_empty[kMaxStagesA];
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) tc_igemm2s_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                 const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  pdl_launch_dependents();
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int BK = 128;
-  constexpr int kSubBh = (BN / 2) * BK;
-  constexpr uint32_t NACC = num_acc<BN>();
-  uint8_t* sB = smem;                                            // [stages][BN/2 x 128]
-  uint8_t* sS = smem + (size_t)p.stages * kSubBh;                // [stages_a][136 x 128]
-  TcControlS<BN>* cs = reinterpret_cast<TcControlS<BN>*>(sS + (size_t)p.stages_a * kStripBytes);
-  TcControl<BN>* ctl = &cs->c;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crank = (int)(blockIdx.x & 1);
-  const bool leader = crank == 0;
-  const int mn_tiles = p.tiles_mp * p.tiles_n;
-  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
-  const uint32_t strip_bytes = (uint32_t)(BM + p.kw - 1) * BK;   // bytes one strip load delivers
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tmA);
-    ptx::prefetch_tensormap(&tmB);
-    for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&ctl->full[s], 1);
-      ptx::mbar_init(&ctl->empty[s], 1);
-    }
-    for (int s = 0; s < p.stages_a; ++s) {
-      ptx::mbar_init(&cs->a_full[s], 1);
-      ptx::mbar_init(&cs->a_empty[s], 1);
-    }
-    for (int b = 0; b < (int)NACC; ++b) {
-      ptx::mbar_init(&ctl->tmem_full[b], 1);
-      ptx::mbar_init(&ctl->tmem_empty[b], 2 * kEpiWarps);
-    }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) ptx::tmem_alloc_2cta(&ctl->tmem_slot, tmem_cols<BN>());
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_slot;
-  ptx::cluster_sync_all();
-  pdl_wait();
-
-  if (warp == 0) {
-    // ===== producer (both CTAs): one A strip per (filter row, channel block), kw weight blocks =====
-    if (lane == 0) {
-      uint32_t itb = 0, ita = 0;
-      bool alive = true;
-      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step) {
-        const int mtile = min((tile / p.tiles_n) * 2 + crank, p.tiles_m - 1);
-        const int m0 = mtile * BM, n0 = (tile % p.tiles_n) * BN;
-        const int q = m0 % p.owp, r = m0 / p.owp;
-        const int bw = q - p.pad, bh = (r % p.oh) - p.pad, bimg = r / p.oh;
-        for (int ky = 0; ky < p.kh && alive; ++ky) {
-          for (int cb = 0; cb < p.cblocks && alive; ++cb, ++ita) {
-            const int sa = ita % p.stages_a;
-            const uint32_t pha = (ita / p.stages_a) & 1;
-            if (!ptx::mbar_wait(&cs->a_empty[sa], pha ^ 1)) { atomicCAS(&g_tc_error, 0, 6); alive = false; break; }
-            if (leader) ptx::mbar_arrive_expect_tx(&cs->a_full[sa], 2u * strip_bytes);
-            ptx::tma_load_im2col_4d_2cta(sS + (size_t)sa * kStripBytes, &tmA, &cs->a_full[sa], cb * BK, bw, bh, bimg, 0,
-                                         (uint16_t)ky);
-            for (int kx = 0; kx < p.kw; ++kx, ++itb) {
-              const int s = itb % p.stages;
-              const uint32_t ph = (itb / p.stages) & 1;
-              if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
-              if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], 2u * (uint32_t)kSubBh);
-              ptx::tma_load_2d_2cta(sB + (size_t)s * kSubBh, &tmB, &ctl->full[s],
-                                    ((ky * p.kw + kx) * p.cblocks + cb) * BK, n0 + crank * (BN / 2));
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (even CTA): tap kx = the strip read kx rows further down =====
-    if (lane == 0 && leader) {
-      constexpr uint32_t idesc = ptx::make_idesc_i8(2 * BM, BN);
-      const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
-      uint32_t itb = 0, ita = 0, acc_it = 0;
-      bool alive = true;
-      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step, ++acc_it) {
-        const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
-        if (!ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + slot * acc_stride<BN>();
-        uint32_t accf = 0;
-        for (int ky = 0; ky < p.kh && alive; ++ky) {
-          for (int cb = 0; cb < p.cblocks && alive; ++cb, ++ita) {
-            const int sa = ita % p.stages_a;
-            const uint32_t pha = (ita / p.stages_a) & 1;
-            if (!ptx::mbar_wait(&cs->a_full[sa], pha)) { atomicCAS(&g_tc_error, 0, 7); alive = false; break; }
-            ptx::tc_fence_after();
-            const uint32_t strip = ptx::smem_u32(sS + (size_t)sa * kStripBytes);   // 1 KB aligned
-            for (int kx = 0; kx < p.kw; ++kx, ++itb) {
-              const int s = itb % p.stages;
-              const uint32_t ph = (itb / p.stages) & 1;
-              if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
-              ptx::tc_fence_after();
-              // start address kx rows into the strip. The 128-byte swizzle is a function of the absolute
-              // shared-memory address, so a row-shifted start needs NO descriptor base offset (measured:
-              // setting the base-offset field to the row position gives wrong accumulators)
-              const uint32_t a_lo = ptx::smem_desc_lo(strip + (uint32_t)kx * BK);
-              const uint32_t a_hi = desc_hi;
-              const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(sB + (size_t)s * kSubBh));
-#pragma unroll
-              for (int k = 0; k < BK / 32; ++k) {
-                ptx::mma_i8_ss_lohi_2cta(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), a_hi, b_lo + (uint32_t)((k * 32) >> 4),
-                                         desc_hi, idesc, accf);
-                accf = 1;
-              }
-              ptx::tc_commit_2cta_multicast(&ctl->empty[s], 3);
-            }
-            if (alive) ptx::tc_commit_2cta_multicast(&cs->a_empty[sa], 3);   // strip free in both CTAs
-          }
-        }
-        if (alive) ptx::tc_commit_2cta_multicast(&ctl->tmem_full[slot], 3);
-      }
-      if (!alive)
-        for (int b = 0; b < (int)NACC; ++b) { ptx::mbar_arrive(&ctl->tmem_full[b]); ptx::mbar_arrive_remote(&ctl->tmem_full[b], 1); }
-    }
-  } else {
-    // ===== epilogue (both CTAs): rows are positions of the padded enumeration =====
-    const int quad = warp & 3;
-    const int et = threadIdx.x - 64;
-    const float rcp = __frcp_rn(p.ep.sc);
-    uint32_t tcount = 0, acc_it = 0;
-    for (int tile = tile0; tile < mn_tiles; tile += tile_step, ++tcount, ++acc_it) {
-      const uint32_t ob = tcount & 1;
-      const int mtile = (tile / p.tiles_n) * 2 + crank;
-      const bool tile_valid = mtile < p.tiles_m;
-      const int m0 = min(mtile, p.tiles_m - 1) * BM, n0 = (tile % p.tiles_n) * BN;
-      for (int j = et; j < BN; j += 32 * kEpiWarps) {
-        const int n = n0 + j;
-        ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
-        ctl->bias[ob][j] = 0.f;
-      }
-      epi_bar_sync();
-      const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
-      const int mp = m0 + quad * 32 + lane;               // position in the padded enumeration
-      const int q = mp % p.owp, rr = mp / p.owp;
-      const int pr = rr % p.oh, img = rr / p.oh;
-      const bool row_valid = tile_valid && mp < p.Mp && q < p.ow;
-      const long long m = ((long long)img * p.oh + pr) * p.ow + q;   // reference row index (conv2d.cc:39-42)
-      const uint32_t t_row = tmem_base + slot * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
-      const int32_t* corr = nullptr;
-      if (p.border_tab && row_valid) {
-        const int y0 = pr - p.pad, x0 = q - p.pad;
-        const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
-        const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
-        const int d = p.pad + 1;
-        const int cls = ((th * d + bh) * d + tw) * d + bw;
-        if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
-      }
-      const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
-      if (!ok) atomicCAS(&g_tc_error, 0, 3);
-      ptx::tc_fence_after();
-      epilogue_row<BN>(p, t_row, (row_valid && ok) ? m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
-                       ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) ptx::mbar_arrive(&ctl->tmem_empty[slot]);
-        else ptx::mbar_arrive_remote(&ctl->tmem_empty[slot], 0);
-      }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::cluster_sync_all();
   if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols<BN>());
 }
 
@@ -993,7 +791,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
         const uint32_t s = it % (uint32_t)sp.f_stages;
         const uint32_t ph = (it / (uint32_t)sp.f_stages) & 1;
-        if (!ptx::mbar_wait(&f_empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+        if (!ptx::mbar_wait(&f_empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
         const int r0 = 4 * p0 - sp.pad;                 // image row of tile row 0
         int lo = r0 < 0 ? -r0 : 0, hi = sp.h - r0;      // tile rows [lo, hi) lie inside the image
         if (hi > rows_per_tile) hi = rows_per_tile;
@@ -1017,7 +815,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
       const uint32_t s = it % (uint32_t)sp.stages;
       const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
-      if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); alive = false; break; }
+      if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
       const int i0 = 4 * p0;
       int nrows = sp.hp - i0;
       if (nrows > rows_per_tile) nrows = rows_per_tile;
@@ -1043,14 +841,14 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     const uint32_t b_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sW));
     const uint32_t sa_base = ptx::smem_u32(sA);
     bool alive = ptx::mbar_wait(w_full, 0);
-    if (!alive) atomicCAS(&g_tc_error, 0, 5);
+    if (!alive) tc_fail(5);
     uint32_t it = 0;
     for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
       const uint32_t buf = it & 1, bph = (it >> 1) & 1;
       const uint32_t s = it % (uint32_t)sp.stages;
       const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
-      if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { atomicCAS(&g_tc_error, 0, 4); alive = false; break; }
-      if (!ptx::mbar_wait(&ctl->full[s], ph)) { atomicCAS(&g_tc_error, 0, 2); alive = false; break; }
+      if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { tc_fail(4); alive = false; break; }
+      if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tbase + buf * acc_stride<BN>();
       const uint32_t a_lo0 = (((sa_base + s * (uint32_t)a_stage) & 0x3FFFFu) >> 4) | a_flags;
@@ -1119,8 +917,8 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       if (nrows > rows_per_tile) nrows = rows_per_tile;
       const bool first = tile == t_begin || p0 == 0;
       // (a timed-out warp keeps walking the loop without waiting, so that nobody hangs in bar.sync)
-      if (!dead && !ptx::mbar_wait(&f_full[fs], fph)) { atomicCAS(&g_tc_error, 0, 6); dead = true; }
-      if (!dead && !ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { atomicCAS(&g_tc_error, 0, 1); dead = true; }
+      if (!dead && !ptx::mbar_wait(&f_full[fs], fph)) { tc_fail(6); dead = true; }
+      if (!dead && !ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); dead = true; }
       // every converter warp is done with the previous tile: its rows can be read, and the stage
       // before it (this tile's target) is no longer being read by a slower warp's copy
       asm volatile("bar.sync 2, %0;" ::"n"(32 * kProdW) : "memory");
@@ -1221,7 +1019,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const bool valid = (prow < sp.oh) && (q < sp.ow);
       const long long m = valid ? ((long long)img * sp.oh + prow) * sp.ow + q : -1ll;
       const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
-      if (!ok) atomicCAS(&g_tc_error, 0, 3);
+      if (!ok) tc_fail(3);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
       if (!(sp.dbg & 1)) {
@@ -1453,10 +1251,9 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
     I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  const int tiles = p.tiles_mp * p.tiles_n * p.splits;          // cluster tiles
-  const int max_clusters = num_sms() / p.cluster;
-  const int grid = (tiles < max_clusters ? tiles : max_clusters) * p.cluster;
-  launch_cluster_pdl(p.cluster, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
 
@@ -1486,10 +1283,7 @@ int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaS
   const int smem = stages * kStage + ctl_bytes + 1024;
   p.tiles_m = (p.M + BM * p.mt - 1) / (BM * p.mt);
   p.tiles_n = (p.out_cp + BN - 1) / BN;
-  const int want_cluster = p.cluster < 1 ? 1 : p.cluster;
-  if (p.cluster < 1 || p.mt != 1 || p.splits > 1) p.cluster = 1;
-  I8IE_REQUIRE(p.cluster == want_cluster, "tcgen05: a %d-CTA cluster needs single 128-row tiles without split-K", want_cluster);
-  p.tiles_mp = (p.tiles_m + p.cluster - 1) / p.cluster;
+  p.tiles_mp = p.tiles_m;
   if (p.splits < 1) { p.splits = 1; p.kb_per = p.num_kb; }
   if constexpr (kHasMT2) {
     if (p.mt == 2) return launch_kernel<BN, BK, MODE, 2>(tmA, tmB, p, smem, stream);
@@ -1533,7 +1327,7 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, c
   I8IE_REQUIRE(stages >= 2, "tcgen05 pair: no room for a pipeline");
   p.stages = stages;
   const int smem = stages * kStage + ctl_bytes + 1024;
-  p.mt = 1; p.splits = 1; p.kb_per = p.num_kb; p.cluster = 2;
+  p.mt = 1; p.splits = 1; p.kb_per = p.num_kb;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.out_cp + BN - 1) / BN;
   p.tiles_mp = (p.tiles_m + 1) / 2;
@@ -1548,35 +1342,6 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, c
   const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
   launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm2_kernel");
-}
-
-// strip variant of the CTA-pair launch (see tc_igemm2s_kernel)
-template <int BN>
-int launch_pair_strip_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
-  constexpr int kMaxSmem = 227 * 1024;
-  const int ctl_bytes = (int)sizeof(TcControlS<BN>);
-  const int kSubBh = (BN / 2) * 128;
-  p.stages_a = 3;
-  int stages = (kMaxSmem - 1024 - ctl_bytes - p.stages_a * kStripBytes) / kSubBh;
-  if (stages > kMaxStages) stages = kMaxStages;
-  I8IE_REQUIRE(stages >= 3, "tcgen05 strip pair: no room for a pipeline");
-  p.stages = stages;
-  const int smem = stages * kSubBh + p.stages_a * kStripBytes + ctl_bytes + 1024;
-  p.mt = 1; p.splits = 1; p.kb_per = p.num_kb; p.cluster = 2;
-  p.tiles_m = (p.Mp + BM - 1) / BM;
-  p.tiles_n = (p.out_cp + BN - 1) / BN;
-  p.tiles_mp = (p.tiles_m + 1) / 2;
-  static int attr_smem = 0;
-  auto kern = tc_igemm2s_kernel<BN>;
-  if (attr_smem < smem) {
-    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
-  const int tiles = p.tiles_mp * p.tiles_n;
-  const int max_clusters = num_sms() / 2;
-  const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
-  launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
-  return check_launch("tc_igemm2s_kernel");
 }
 
 // sub-blocks per pipeline stage: short K blocks are batched so that one mbarrier round trip
@@ -1641,34 +1406,6 @@ int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& 
   return encode_im2col_4d(tm, x, g, bk);
 }
 
-// A-strip view (tc_igemm2s_kernel): tap (0, ky) only, output positions enumerated over the padded
-// width (upper corner +pad, as if kw were 1), 128 + kw - 1 positions per load.
-int tc_encode_act_map_strip(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g) {
-  static EncodeIm2colFn fn = driver_fn<EncodeIm2colFn>("cuTensorMapEncodeIm2col");
-  I8IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col entry point not available");
-  cuuint64_t dims[4] = {(cuuint64_t)g.cp, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
-  cuuint64_t strides[3] = {(cuuint64_t)g.cp, (cuuint64_t)g.cp * g.w, (cuuint64_t)g.cp * g.w * g.h};
-  int lower[2] = {-g.pad, -g.pad};
-  int upper[2] = {g.pad, g.pad - (g.kh - 1)};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x), dims, strides, lower, upper, 128,
-                  (cuuint32_t)(BM + g.kw - 1), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  I8IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col (strip view) failed (%d): c=%d w=%d h=%d n=%d k=%dx%d p=%d",
-               (int)r, g.cp, g.w, g.h, g.n, g.kh, g.kw, g.pad);
-  return I8IE_OK;
-}
-
-bool tc_conv_strip_eligible(const GemmGeom& g, int bk, int bn) {
-  // measured on B200: bit-exact but slower than the plain pair kernel (545 vs 402 us for conv2 at
-  // batch 1000; the padded enumeration adds 15 % tiles and the operand ingest it saves is not what
-  // bounds the pair kernel) -> opt-in only
-  if (std::getenv("I8IE_STRIP") == nullptr) return false;
-  const long long mp = (long long)g.n * g.oh * (g.w + 2 * g.pad);
-  return tc_conv_cluster(bk, bn) == 2 && g.stride == 1 && g.kw >= 2 && g.kw <= kStripRows - BM + 1 && g.cp % 128 == 0 &&
-         mp < (1ll << 31) - 256;
-}
-
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx) {
   return encode_tiled_2d(tm, x, (uint64_t)k, (uint64_t)m, (uint64_t)ldx, 128, BM);
 }
@@ -1676,15 +1413,12 @@ int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int 
 int tc_pick_bn(int n) { return pick_bn(n); }
 
 // Cluster mode of a conv plan: 1 = single CTAs; 2 = CTA pairs, tcgen05.mma.cta_group::2 with the
-// weight tile split across the pair (default for wide tiles); 3 = 2-CTA clusters of independent
-// 128-row tiles with the weight tile TMA-multicast (opt-in I8IE_CLUSTER_MC=1: measured slower, the
-// bound is the per-SM ingest, which multicast does not reduce). For 2 and 3 the weight tensor map's
-// box holds bn / 2 rows (whole 1 KB swizzle atoms).
+// weight tile split across the pair (wide tiles with 128-byte K blocks; the weight tensor map's box
+// then holds bn / 2 rows = whole 1 KB swizzle atoms). I8IE_NO_CLUSTER=1 forces single CTAs (tests).
 int tc_conv_cluster(int bk, int bn) {
   if (std::getenv("I8IE_NO_CLUSTER") != nullptr) return 1;
   const bool ok = bk == 128 && (bn == 256 || bn == 192 || bn == 128) && ((bn / 2) * bk) % 1024 == 0;
-  if (!ok) return 1;
-  return std::getenv("I8IE_CLUSTER_MC") != nullptr ? 3 : 2;
+  return ok ? 2 : 1;
 }
 
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
@@ -1697,17 +1431,6 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
-  if (cluster == 4) {   // CTA pairs with A strips (stride 1)
-    p.owp = g.w + 2 * g.pad;
-    p.Mp = g.n * g.oh * p.owp;
-    switch (bn) {
-      case 128: return launch_pair_strip_bn<128>(tmA, tmB, p, stream);
-      case 192: return launch_pair_strip_bn<192>(tmA, tmB, p, stream);
-      case 256: return launch_pair_strip_bn<256>(tmA, tmB, p, stream);
-    }
-    set_error("tcgen05 strip pair: unsupported BN %d", bn);
-    return I8IE_EINVAL;
-  }
   if (cluster == 2) {   // CTA pairs
     I8IE_REQUIRE(bk == 128, "tcgen05 pair: needs 128-byte K blocks");
     switch (bn) {
@@ -1718,8 +1441,7 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
     set_error("tcgen05 pair: unsupported BN %d", bn);
     return I8IE_EINVAL;
   }
-  p.cluster = cluster == 3 ? 2 : 1;
-  p.mt = p.cluster > 1 ? 1 : 2;   // launch_cfg falls back to 1 when the shape is too small for it
+  p.mt = 2;   // launch_cfg falls back to 1 when the shape is too small for it
   return launch_bk<1>(bk, bn, tmA, tmB, p, stream);
 }
 
@@ -1937,12 +1659,70 @@ int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   return I8IE_EINVAL;
 }
 
+// ---- protocol-error sink -------------------------------------------------------------------------
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex g_sink_mu;
+int* g_sink_host[kMaxDevices] = {};   // pinned, mapped; one int per device
+int* g_sink_dev[kMaxDevices] = {};    // the same words as device addresses
+}  // namespace
+
+// Creates the current device's host-mapped error flag and publishes its device address to the
+// kernels. Synchronising calls inside: must run outside of stream capture (plan creation and
+// i8ie_device_check() call it; a model's eager warm-up calls always precede its graph capture).
+int tc_error_sink_init() {
+  int dev = 0;
+  I8IE_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return I8IE_OK;
+  std::lock_guard<std::mutex> lk(g_sink_mu);
+  if (g_sink_host[dev] != nullptr) return I8IE_OK;
+  int* h = nullptr;
+  I8IE_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+  *h = 0;
+  int* d = nullptr;
+  I8IE_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0));
+  I8IE_CUDA_OK(cudaMemcpyToSymbol(g_tc_error_host, &d, sizeof(d)));
+  g_sink_dev[dev] = d;
+  g_sink_host[dev] = h;
+  return I8IE_OK;
+}
+
+// Device address of the current device's flag (nullptr before tc_error_sink_init): kernels of other
+// translation units (the peer result exchange) report their bounded-wait timeouts through it.
+int* tc_error_sink_device_ptr() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  return g_sink_dev[dev];
+}
+
+// Called on the launch paths: creates the sink on first use unless the stream is capturing.
+void tc_error_sink_touch(cudaStream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || g_sink_host[dev] != nullptr) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  tc_error_sink_init();
+}
+
+// First protocol error recorded on the current device since the last reset (0 = none). Plain host
+// memory read: meaningful after the work in question has been synchronised.
+int tc_error_poll(bool reset) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  int* h = g_sink_host[dev];
+  if (h == nullptr) return 0;
+  const int v = *reinterpret_cast<volatile int*>(h);
+  if (reset && v != 0) *reinterpret_cast<volatile int*>(h) = 0;
+  return v;
+}
+
 int tc_read_error(int* out, bool reset) {
   int v = 0;
   I8IE_CUDA_OK(cudaMemcpyFromSymbol(&v, g_tc_error, sizeof(int)));
   if (reset && v != 0) {
     const int z = 0;
     I8IE_CUDA_OK(cudaMemcpyToSymbol(g_tc_error, &z, sizeof(int)));
+    tc_error_poll(true);
   }
   *out = v;
   return I8IE_OK;

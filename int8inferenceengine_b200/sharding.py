@@ -130,3 +130,160 @@ class ResultExchange:
             if self._side is not None:
                 self._done[k] = run_on.record_event()
         return self.logits_all, self.agree
+
+
+class PeerExchange:
+    """The same result exchange over NVLink / NVSwitch PEER MEMORY instead of NCCL
+    (csrc/peer_exchange.cu): the pack kernel pushes this rank's [count | logits] chunk into every
+    rank's gather buffer with peer stores and publishes a step number; the unpack kernel waits for
+    all ranks' step numbers and unpacks from local memory. Two kernels, no host call and no NCCL
+    collective per step, so a whole step (forward + exchange) is capturable as ONE CUDA graph —
+    see ShardedStep. torch.distributed is used once, at construction, to swap the 64-byte CUDA IPC
+    handles. Same call contract as ResultExchange."""
+
+    def __init__(self, global_batch: int, cols: int, device):
+        import ctypes as C
+        from . import _lib
+        self._C = C
+        self._L = _lib.load()
+        self._check = _lib.check
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.global_batch, self.cols = int(global_batch), int(cols)
+        self.device = torch.device(device)
+        spans = [shard_range(global_batch, r, self.world) for r in range(self.world)]
+        self.rows = spans[self.rank][1] - spans[self.rank][0]
+        cap = max(hi - lo for lo, hi in spans)
+        while (cap * cols) % 4:
+            cap += 1
+        self.chunk = int(self._L.i8ie_top1_chunk_bytes(cap, cols))
+        nbytes = int(self._L.i8ie_peer_exchange_bytes(self.world, self.chunk))
+        mine = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            self._check(self._L.i8ie_peer_alloc(nbytes, C.byref(mine), handle), "peer_alloc")
+        self._mine = mine.value
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle))
+        self._opened = []
+        bases = (C.c_void_p * self.world)()
+        for p in range(self.world):
+            if p == self.rank:
+                bases[p] = self._mine
+                continue
+            ptr = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+            with torch.cuda.device(self.device):
+                self._check(self._L.i8ie_peer_open(buf, C.byref(ptr)), f"peer_open(rank {p})")
+            bases[p] = ptr.value
+            self._opened.append(ptr.value)
+        self._bases = bases
+        self.seq = torch.zeros(2, dtype=torch.int64, device=self.device)    # [0] = step counter
+        self.logits_all = torch.empty(self.global_batch, cols, dtype=torch.float32, device=self.device)
+        self.agree = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.barrier()          # every buffer exists, is zeroed and is mapped everywhere before the first push
+
+    def wait(self):
+        pass
+
+    def __call__(self, local_logits: torch.Tensor, ref_argmax: torch.Tensor | None = None):
+        if not local_logits.is_cuda or local_logits.dtype != torch.float32 or not local_logits.is_contiguous():
+            raise ValueError("PeerExchange needs a contiguous fp32 CUDA tensor")
+        if tuple(local_logits.shape) != (self.rows, self.cols):
+            raise ValueError(f"expected logits of shape {(self.rows, self.cols)}, got {tuple(local_logits.shape)}")
+        ref_ptr = None
+        if ref_argmax is not None:
+            if ref_argmax.dtype != torch.int64 or ref_argmax.numel() != self.rows or not ref_argmax.is_cuda:
+                raise ValueError("ref_argmax must be int64 CUDA with one entry per local row")
+            ref_ptr = ref_argmax.data_ptr()
+        st = torch.cuda.current_stream().cuda_stream
+        self._check(self._L.i8ie_top1_pack_push(local_logits.data_ptr(), ref_ptr, self.rows, self.cols, self._bases,
+                                                self.world, self.rank, self.chunk, self.seq.data_ptr(), st),
+                    "top1_pack_push")
+        self._check(self._L.i8ie_top1_wait_unpack(self._mine, self.world, self.chunk, self.seq.data_ptr(),
+                                                  self.logits_all.data_ptr(), self.agree.data_ptr(), st),
+                    "top1_wait_unpack")
+        return self.logits_all, self.agree
+
+    def close(self):
+        """Unmaps the peers' buffers and frees the local one (collective: all ranks call it)."""
+        if self._mine is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier()          # nobody is still pushing into a buffer that is about to go away
+        with torch.cuda.device(self.device):
+            for ptr in self._opened:
+                self._L.i8ie_peer_close(ptr)
+            self._opened = []
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier()
+            self._L.i8ie_peer_free(self._mine)
+        self._mine = None
+
+
+def make_exchange(global_batch: int, cols: int, device, kind: str | None = None):
+    """Result exchange for the sharded step: 'peer' (NVLink peer memory, default on GPUs) or 'nccl'
+    (ResultExchange). I8IE_EXCHANGE overrides."""
+    import os
+    kind = kind or os.environ.get("I8IE_EXCHANGE", "peer")
+    if kind == "peer":
+        return PeerExchange(global_batch, cols, device)
+    if kind == "nccl":
+        return ResultExchange(global_batch, cols, device)
+    raise ValueError(f"unknown exchange kind {kind!r}")
+
+
+class ShardedStep:
+    """One batch-sharded step = the rank's quantised forward + the result exchange, captured as ONE
+    CUDA graph per input buffer: a step is a single host enqueue (graph launch), whatever the number
+    of kernels, and nothing on the host sits between the forward and the exchange.
+
+    model     an i8ie.Module (converted); its own graph replay is bypassed (the forward is captured here)
+    inputs    list of i8ie.Tensor device batches [rows, ...] (static buffers: replays read them in place)
+    ref_args  list of int64 CUDA tensors [rows] (reference argmax per input) or None
+    exchange  PeerExchange (or ResultExchange: NCCL inside the capture)"""
+
+    def __init__(self, model, inputs, ref_args, exchange):
+        self.model, self.inputs, self.exchange = model, list(inputs), exchange
+        self.ref_args = list(ref_args) if ref_args is not None else [None] * len(self.inputs)
+        self.graphs = []
+        self.kernels_per_step = 0
+        self.replays = 0
+        from . import _lib
+        rows, cols = exchange.rows, exchange.cols
+        saved = model.graph
+        model.graph = False
+        try:
+            pool = None
+            for x, ref in zip(self.inputs, self.ref_args):
+                for _ in range(2):          # eager warm-up: plans, offsets, packed weights, scratch sizes
+                    out = model(x)
+                    exchange(out.data.buf.view(rows, cols), ref)
+                torch.cuda.synchronize()
+                before = _lib.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    out = model(x)
+                    exchange(out.data.buf.view(rows, cols), ref)
+                self.kernels_per_step = int(_lib.launch_count() - before)
+                pool = pool or g.pool()
+                self.graphs.append((g, out))
+        finally:
+            model.graph = saved
+
+    def __call__(self, i: int):
+        """Runs step i (input i modulo the ring). Returns the exchange's static result buffers
+        (logits of all ranks, agreement count), valid until the next step."""
+        self.graphs[i % len(self.graphs)][0].replay()
+        self.replays += 1
+        return self.exchange.logits_all, self.exchange.agree
+
+    def local_logits(self, i: int):
+        """The rank's own dequantised logits of the last replay of input i (static graph output)."""
+        return self.graphs[i % len(self.graphs)][1].data.buf
+
+    def launches(self):
+        return self.replays * self.kernels_per_step

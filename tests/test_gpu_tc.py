@@ -118,12 +118,26 @@ def test_tc_conv_cta_pair(geom):
     _run_conv_parity(geom)
 
 
-@pytest.mark.parametrize("variant", ["I8IE_NO_CLUSTER", "I8IE_CLUSTER_MC", "I8IE_STRIP"])
 @pytest.mark.parametrize("geom", [PAIR[2], PAIR[3], PAIR[5]])
-def test_tc_conv_cluster_variants(geom, variant, monkeypatch):
-    """The opt-in variants of the same layers stay bit-exact: single CTAs, 2-CTA clusters with the
-    weight tile multicast, and the stride-1 A-strip pair kernel (taps walked by descriptor offsets)."""
-    monkeypatch.setenv(variant, "1")
+def test_tc_conv_single_cta_variant(geom, monkeypatch):
+    """The same layers through the single-CTA kernel (I8IE_NO_CLUSTER=1) stay bit-exact."""
+    monkeypatch.setenv("I8IE_NO_CLUSTER", "1")
+    _run_conv_parity(geom)
+
+
+PAIR_WRAP = [  # more pair tiles than the 74 clusters of the persistent grid, odd tails: every cluster runs several
+    # tiles, so the TMEM accumulator ring wraps, tmem_full / tmem_empty flip phase and the TMA ring runs ahead
+    # across tile boundaries — all checked against the oracle (s32 accumulators and u8)
+    (40, 96, 27, 27, 256, 5, 1, 2),      # AlexNet conv2: 228 M tiles -> 114 pair tiles, 1 N tile
+    (130, 256, 13, 13, 384, 3, 1, 1),    # AlexNet conv3: 172 M tiles -> 86 pair tiles x 2 N tiles of 192
+    (125, 384, 13, 13, 256, 3, 1, 1),    # AlexNet conv5 at the 8-GPU shard size: 166 M tiles (83 pairs, last one ragged)
+    (61, 384, 13, 13, 384, 3, 1, 1),     # AlexNet conv4: 81 M tiles (odd) -> 41 pair tiles x 2, tail pair half empty
+    (140, 128, 17, 19, 320, 3, 2, 1),    # stride 2, N = 320 at pitch 384 -> 50 pair tiles x 2 N tiles of 192, ragged N tail
+]
+
+
+@pytest.mark.parametrize("geom", PAIR_WRAP)
+def test_tc_conv_cta_pair_many_tiles(geom):
     _run_conv_parity(geom)
 
 
