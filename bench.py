@@ -579,6 +579,7 @@ def run_ours(args):
                 return "tc_igemm_kernel / fc_head_kernel (fully_connected)"
             return {3: "tc_stem2_kernel (fused input quantise + stem conv)",
                     2: "tc_igemm2_kernel (CTA-pair tcgen05 implicit GEMM + fused requant epilogue)",
+                    4: "tc_igemm2_kernel (CTA-pair tcgen05 implicit GEMM + fused requant epilogue)",
                     1: "simt_igemm_kernel"}.get(impl, "tc_igemm_kernel")
         groups = {}
         for r in layer_rows:

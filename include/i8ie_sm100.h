@@ -164,6 +164,13 @@ I8IE_API int i8ie_relu_u8(const uint8_t* x, uint8_t* y, int64_t n, int zp, void*
  * x.reshape(-1, c*oh*ow) needs, tensor.h:106-133). */
 I8IE_API int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int c, int cp,
                          int ksize, int stride, int out_nchw, void* stream);
+/* The same pooling into a PHYSICALLY PADDED NHWC tensor y[n][oh + 2*out_pad][ow + 2*out_pad][out_cp]:
+ * border pixels hold pad_value (the tensor's zero point: conv2d.cc:24-25 pads im2col with in.zero_point),
+ * channel pitch out_cp (c <= out_cp <= cp, multiple of 16). Feeds the "row mode" convolution plans
+ * (i8ie_conv2d_plan_create impl 4). ksize = stride = 1 is a plain pad-copy of an NHWC tensor. */
+I8IE_API int i8ie_maxpool_u8_nhwc_padded(const uint8_t* x, uint8_t* y, int n, int h, int w, int c, int cp,
+                                         int ksize, int stride, int out_cp, int out_pad, int pad_value,
+                                         void* stream);
 
 /* Layout glue for the NCHW-facing API (tensor.h:40-47 / pybind11.cc:14-15). */
 I8IE_API int i8ie_u8_nchw_to_nhwc(const uint8_t* x, uint8_t* y, int n, int c, int h, int w, int cp, int pad_value, void* stream);
@@ -201,13 +208,20 @@ typedef struct i8ie_conv_plan i8ie_conv_plan;
  * outlive the plan. x is NHWC u8 with pitch cp; y is NHWC u8 with pitch
  * out_cp (multiple of 16, >= kc). Replaces im2col (conv2d.cc:34-49), the
  * per-image cblas_gemm_s8u8s32 (:131-133), down_scale (:134-135) and transpose (:136).
- * impl: 0 = auto, 1 = force the SIMT dp4a kernel, 2 = force tcgen05 (error if ineligible). */
+ * impl: 0 = auto, 1 = force the SIMT dp4a kernel, 2 = force tcgen05 (error if ineligible),
+ * 4 = tcgen05 ROW MODE: x is then the PHYSICALLY PADDED tensor [n][h + 2*pad][w + 2*pad][cp] whose border
+ * holds in.zero_point (i8ie_maxpool_u8_nhwc_padded writes it) followed by >= 128 readable bytes, and cp must
+ * be i8ie_conv2d_row_mode_cp(...) (!= 0). The GEMM K index is (filter row, byte of the contiguous kw * cp
+ * run) instead of (tap, channel padded to 128): fewer K blocks when c is not a multiple of 128. */
 I8IE_API i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int kc, int kh, int kw,
                                         int stride, int pad, int out_cp, const int8_t* w_packed,
                                         int kc_pad, int impl);
 I8IE_API void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan);
+/* Channel pitch the padded input of a row-mode plan must have, or 0 when the layer should use the plain
+ * plans (stride != 1, narrow N, or no K saved). cp_plain = the pitch the plain NHWC tensor would have. */
+I8IE_API int i8ie_conv2d_row_mode_cp(int c, int cp_plain, int kh, int kw, int stride, int pad, int out_cp);
 /* Which kernel the plan resolved to: 1 = SIMT dp4a, 2 = tcgen05 (TMA im2col), 3 = tcgen05 stem
- * (small-C strided first layer: the plan owns a bordered superpixel copy of the input). */
+ * (small-C strided first layer: the plan owns a bordered superpixel copy of the input), 4 = tcgen05 row mode. */
 I8IE_API int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan);
 /* y = requant(conv(x) + oc) [+relu]; sa=in.scale, sb=weight scale, sc=layer scale_,
  * zp_in = in.zero_point (spatial padding value, conv2d.cc:129-130), zp_out = layer

@@ -22,6 +22,7 @@ SYMBOLS = [
     "i8ie_conv2d_f32", "i8ie_linear_f32", "i8ie_relu_f32", "i8ie_maxpool_f32_nchw",
     "i8ie_tc_error_poll", "i8ie_peer_exchange_bytes", "i8ie_peer_alloc", "i8ie_peer_open", "i8ie_peer_close",
     "i8ie_peer_free", "i8ie_top1_pack_push", "i8ie_top1_wait_unpack",
+    "i8ie_maxpool_u8_nhwc_padded", "i8ie_conv2d_row_mode_cp",
 ]
 
 _lib = None
@@ -59,6 +60,8 @@ def load():
     L.i8ie_range_from_minmax_host.argtypes = [f, f, C.POINTER(f), C.POINTER(C.c_uint8)]
     L.i8ie_relu_u8.argtypes = [vp, vp, i64, i, vp]
     L.i8ie_maxpool_u8_nhwc.argtypes = [vp, vp, i, i, i, i, i, i, i, i, vp]
+    L.i8ie_maxpool_u8_nhwc_padded.argtypes = [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]
+    L.i8ie_conv2d_row_mode_cp.argtypes = [i, i, i, i, i, i, i]
     L.i8ie_u8_nchw_to_nhwc.argtypes = [vp, vp, i, i, i, i, i, i, vp]
     L.i8ie_u8_nhwc_to_nchw.argtypes = [vp, vp, i, i, i, i, i, vp]
     L.i8ie_quantize_weight_host.argtypes = [vp, i64, vp, i64, vp, vp, C.POINTER(f)]
@@ -110,7 +113,8 @@ def check(rc, what=""):
 _TC_ROLES = {1: "TMA producer waiting for a free operand stage", 2: "MMA issuer waiting for operands",
              3: "epilogue waiting for an accumulator", 4: "MMA issuer waiting for a drained accumulator",
              5: "stem MMA issuer waiting for the weights", 6: "stem converter waiting for fp32 rows",
-             7: "result exchange waiting for a peer rank's chunk"}
+             7: "result exchange waiting for a peer rank's chunk",
+             8: "split-K fc CTA waiting for its sibling CTAs' partial tiles"}
 
 
 def check_tc_error():

@@ -179,6 +179,77 @@ def _tensor_from_pinned(h):
     return TensorF32(_ChunkedStorage(dev, chunks), shape)
 
 
+# ---- pageable host arrays (what an unmodified reference script passes): staged through pinned memory ----
+_STAGE = {"bufs": [], "next": 0, "pool": None}
+_STAGE_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
+
+
+def _staging(numel):
+    """One of two pinned staging buffers (so the DMA of one batch can still be running while the next
+    batch is being staged); waits until the buffer's previous DMA has finished."""
+    st = _STAGE
+    if len(st["bufs"]) < 2:
+        st["bufs"].append({"t": None, "ev": None})
+    b = st["bufs"][st["next"] % len(st["bufs"])]
+    st["next"] += 1
+    if b["ev"] is not None:
+        b["ev"].synchronize()
+    if b["t"] is None or b["t"].numel() < numel:
+        b["t"] = torch.empty(numel, dtype=torch.float32).pin_memory()
+    return b
+
+
+def _parallel_copy(dst, src):
+    """dst[:] = src for large contiguous float32 numpy views, split over a few threads (memcpy releases the GIL)."""
+    n = src.size
+    if _STAGE_THREADS == 1 or n < (1 << 20):
+        np.copyto(dst, src)
+        return
+    if _STAGE["pool"] is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _STAGE["pool"] = ThreadPoolExecutor(max_workers=_STAGE_THREADS)
+    step = (n + _STAGE_THREADS - 1) // _STAGE_THREADS
+    futs = [_STAGE["pool"].submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
+    for f in futs:
+        f.result()
+
+
+def _tensor_from_pageable(a):
+    """Contiguous float32 numpy array -> device. The bytes are copied SYNCHRONOUSLY into pinned staging
+    memory (when this returns the caller may modify the array, like tensor.h:40-47), chunk by chunk,
+    and each chunk's host->device DMA is queued as soon as it is staged; Module.__call__ consumes the
+    chunks as they land, exactly as for a pinned source (see _ChunkedStorage)."""
+    global _COPY_STREAM
+    shape = list(a.shape)
+    flat = a.reshape(-1)
+    c = _h2d_chunks(shape[0], flat.size * 4) if len(shape) >= 2 else 1
+    if _COPY_STREAM is None:
+        _COPY_STREAM = torch.cuda.Stream()
+    stage = _staging(flat.size)
+    st_t = stage["t"][:flat.size]
+    st_np = st_t.numpy()
+    cur = torch.cuda.current_stream()
+    dev = torch.empty(flat.size, dtype=torch.float32, device="cuda")
+    dev.record_stream(_COPY_STREAM)
+    _COPY_STREAM.wait_stream(cur)
+    rows = shape[0] // c if c > 1 else shape[0] if shape else 1
+    per = flat.size // shape[0] if (shape and shape[0]) else flat.size
+    chunks = []
+    for k in range(c):
+        lo, hi = (k * rows * per, (k + 1) * rows * per) if c > 1 else (0, flat.size)
+        _parallel_copy(st_np[lo:hi], flat[lo:hi])
+        with torch.cuda.stream(_COPY_STREAM):
+            dev[lo:hi].copy_(st_t[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(_COPY_STREAM)
+        chunks.append((k * rows, (k + 1) * rows, ev) if c > 1 else (0, shape[0] if shape else 1, ev))
+    stage["ev"] = chunks[-1][2]
+    if c == 1:
+        cur.wait_event(chunks[-1][2])
+        return TensorF32(_Storage(dev), shape)
+    return TensorF32(_ChunkedStorage(dev, chunks), shape)
+
+
 def pending_chunks(x):
     """[(sub-batch tensor, copy-done event)] of a float tensor still arriving in chunks, else None."""
     st = x._st
@@ -374,6 +445,26 @@ class TensorU8(_TensorBase):
         # physical NHWC differs from the logical order: materialise the logical order once
         return TensorU8(_Storage(self._dense_buf()), shape, "dense", None, self._scale, self._zp)
 
+    def _as_padded_nhwc(self, n, c, h, w, cpx, pad):
+        """This tensor as a PHYSICALLY PADDED NHWC buffer [n][h + 2*pad][w + 2*pad][cpx] whose border holds
+        the zero point (the operand layout of a row-mode convolution plan). A not-yet-launched max-pool
+        writes it directly; anything else is pad-copied once (cached: tensors are immutable)."""
+        cache = self.__dict__.setdefault("_padded", {})
+        hit = cache.get((cpx, pad))
+        if hit is not None:
+            return hit
+        L = _need_cuda()
+        pool = self._pending("pool")
+        if pool is not None and not pool.out_nchw:
+            out = pool.launch_padded(cpx, pad, self._zp)
+        else:
+            buf, cp = self._as_nhwc(n, c, h, w)
+            out = torch.empty(n * (h + 2 * pad) * (w + 2 * pad) * cpx + 128, dtype=torch.uint8, device=buf.device)
+            check(L.i8ie_maxpool_u8_nhwc_padded(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, 1, 1, cpx, pad,
+                                                self._zp, _stream()), "u8_nhwc pad-copy")
+        cache[(cpx, pad)] = out
+        return out
+
     def _as_nhwc(self, n, c, h, w, want_cp=None):
         """(buffer, cp) of this tensor as NHWC. An NHWC tensor of the right shape is used as it
         is, whatever its pitch (unless want_cp insists); anything else is converted once."""
@@ -429,6 +520,20 @@ class _DeferredPool:
             return _Storage(out), "dense", None
         return _Storage(out), "nhwc", (n, c, oh, ow, cp)
 
+    def launch_padded(self, out_cp, out_pad, zp):
+        """The pool written straight into the physically padded layout a row-mode convolution reads
+        (border = zero point, channel pitch out_cp); + 128 readable bytes behind the tensor."""
+        L = _need_cuda()
+        x, k, s = self.x, self.k, self.s
+        n, c, h, w = x._shape
+        oh, ow = (h - k) // s + 1, (w - k) // s + 1
+        buf, cp = x._as_nhwc(n, c, h, w)
+        out = torch.empty(n * (oh + 2 * out_pad) * (ow + 2 * out_pad) * out_cp + 128, dtype=torch.uint8,
+                          device=buf.device)
+        check(L.i8ie_maxpool_u8_nhwc_padded(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, k, s, out_cp, out_pad,
+                                            int(zp), _stream()), "maxpool_u8_nhwc_padded")
+        return out
+
 
 class _DeferredQuant:
     """Input quantise (module.py:20) that a first-layer stem convolution can fuse."""
@@ -475,6 +580,8 @@ def tensor(ndarray):
             return _tensor_from_pinned(h)
         return TensorF32(_Storage(h.reshape(-1).to("cuda", non_blocking=True)), list(h.shape))
     a = np.ascontiguousarray(np.asarray(ndarray), dtype=np.float32)
+    if a.size * 4 >= H2D_CHUNK_MIN_BYTES and not os.environ.get("I8IE_NO_H2D_CHUNKS"):
+        return _tensor_from_pageable(a)
     t = torch.from_numpy(a.reshape(-1).copy()).to("cuda", non_blocking=False)
     return TensorF32(_Storage(t), list(a.shape))
 
@@ -929,9 +1036,25 @@ class Conv2d(_BaseLayer):
             y = self.forward_quantize_fused(quant.src, quant.scale, quant.zp, relu=relu)
             if y is not None:
                 return y
-        buf, cp = x._as_nhwc(n, c, h, w)
-        oc, _ = self._offsets(x._zp, x.scale(), True)
         out_cp = _act_pitch(kc)
+        oc, _ = self._offsets(x._zp, x.scale(), True)
+        # row mode (stride 1, channel count not a multiple of 128): physically padded input, K = (filter row,
+        # contiguous kw * cp run) — AlexNet conv2 runs 20 K blocks instead of 25
+        cpx = 0
+        if impl == 0:
+            cpx = int(L.i8ie_conv2d_row_mode_cp(c, _act_pitch(c), kh, kw, self._stride, self._pad, out_cp))
+        elif impl == 4:      # forced (tests / probes): plan creation checks the hard constraints
+            cpx = _r16(c)
+        if cpx:
+            xp = x._as_padded_nhwc(n, c, h, w, cpx, self._pad)
+            out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=xp.device)
+            plan = self._plan(n, c, h, w, cpx, 4)
+            self._last_impl = 4
+            check(L.i8ie_conv2d_u8(plan, xp.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
+                                   float(self._w_scale), float(self._scale), x._zp, self._zp, 1 if relu else 0,
+                                   acc_out.data_ptr() if acc_out is not None else None, _stream()), "conv2d_u8 (row mode)")
+            return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
+        buf, cp = x._as_nhwc(n, c, h, w)
         out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=buf.device)
         plan = self._plan(n, c, h, w, cp, impl)
         self._last_impl = int(L.i8ie_conv2d_plan_impl(plan))   # 1 SIMT, 2 tcgen05 im2col, 3 tcgen05 stem

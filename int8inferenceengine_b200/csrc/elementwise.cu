@@ -475,6 +475,37 @@ __global__ void __launch_bounds__(kThreads) maxpool_nhwc_rows_kernel(const uint8
   }
 }
 
+// Same, into a PHYSICALLY PADDED NHWC tensor for a following "row mode" convolution (tc_gemm.cu):
+//   y[img][oh + 2*opad][ow + 2*opad][ocp], border pixels = zp (conv2d.cc:24-25 pads with the input
+// zero point), channel pitch ocp <= cp (only the groups that hold real channels are kept).
+// One block per padded output row; ks = st = 1 makes it a plain pad-copy.
+template <int KS>
+__global__ void __launch_bounds__(kThreads) maxpool_nhwc_rows_padded_kernel(const uint8_t* __restrict__ x,
+                                                                            uint8_t* __restrict__ y, int h, int w,
+                                                                            int c, int cp, int ks_rt, int st, int oh,
+                                                                            int ow, int ocp, int opad, uint32_t zp4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int groups = ocp >> 4;
+  const int ohp = oh + 2 * opad, owp = ow + 2 * opad;
+  const int img = blockIdx.x / ohp, oyp = blockIdx.x - img * ohp;
+  const int oy = oyp - opad;
+  uint8_t* yrow = y + ((int64_t)img * ohp + oyp) * owp * ocp;
+  const uint4 z = make_uint4(zp4, zp4, zp4, zp4);
+  if (oy < 0 || oy >= oh) {
+    for (int t = threadIdx.x; t < owp * groups; t += blockDim.x) reinterpret_cast<uint4*>(yrow)[t] = z;
+    return;
+  }
+  const uint8_t* xrow = x + ((int64_t)img * h + (int64_t)oy * st) * w * cp;
+  for (int t = threadIdx.x; t < owp * groups; t += blockDim.x) {
+    const int oxp = t / groups, g = t - oxp * groups;
+    const int ox = oxp - opad;
+    uint4 m = z;
+    if (ox >= 0 && ox < ow) m = pool_window<KS>(xrow + (int64_t)ox * st * cp + g * 16, w, cp, ks_rt, g * 16 >= c);
+    reinterpret_cast<uint4*>(yrow)[t] = m;
+  }
+}
+
 // Pool + flatten: one block per image; the NCHW-ordered result [c][oh*ow] is assembled in
 // shared memory and written out with coalesced 128-bit stores (it is contiguous per image).
 template <int KS>
@@ -841,6 +872,30 @@ int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int 
   }
 #undef I8IE_POOL_KS
   return check_launch("maxpool_nhwc_kernel");
+}
+
+int i8ie_maxpool_u8_nhwc_padded(const uint8_t* x, uint8_t* y, int n, int h, int w, int c, int cp, int ksize,
+                                int stride, int out_cp, int out_pad, int pad_value, void* stream) {
+  I8IE_REQUIRE(cp % 16 == 0 && cp >= c && out_cp % 16 == 0 && out_cp >= c && out_cp <= cp && ksize >= 1 &&
+                   stride >= 1 && h >= ksize && w >= ksize && out_pad >= 0 && pad_value >= 0 && pad_value <= 255 &&
+                   aligned16(x) && aligned16(y),
+               "maxpool_padded: bad shape/alignment");
+  const int oh = (h - ksize) / stride + 1, ow = (w - ksize) / stride + 1;
+  const int64_t rows = (int64_t)n * (oh + 2 * out_pad);
+  if (rows == 0) return I8IE_OK;
+  I8IE_REQUIRE(rows < (1ll << 30), "maxpool_padded: too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t zp4 = (uint32_t)pad_value * 0x01010101u;
+  if (ksize == 3)
+    launch_pdl(maxpool_nhwc_rows_padded_kernel<3>, dim3((unsigned)rows), dim3(kThreads), 0, s, x, y, h, w, c, cp, ksize,
+               stride, oh, ow, out_cp, out_pad, zp4);
+  else if (ksize == 2)
+    launch_pdl(maxpool_nhwc_rows_padded_kernel<2>, dim3((unsigned)rows), dim3(kThreads), 0, s, x, y, h, w, c, cp, ksize,
+               stride, oh, ow, out_cp, out_pad, zp4);
+  else
+    launch_pdl(maxpool_nhwc_rows_padded_kernel<0>, dim3((unsigned)rows), dim3(kThreads), 0, s, x, y, h, w, c, cp, ksize,
+               stride, oh, ow, out_cp, out_pad, zp4);
+  return check_launch("maxpool_nhwc_rows_padded_kernel");
 }
 
 int i8ie_u8_nchw_to_nhwc(const uint8_t* x, uint8_t* y, int n, int c, int h, int w, int cp, int pad_value,

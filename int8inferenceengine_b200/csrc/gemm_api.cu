@@ -67,6 +67,10 @@ struct i8ie_conv_plan {
   int8_t* stem_w;       // [kc_pad][kh][64]
   CUtensorMap tmA_stem;
   bool stem2;           // smem-resident-row kernel (stride 4, narrow rows)
+  // row mode (impl 4): physically padded input, plan-owned [kc_pad][kh][kr] weights
+  int kr;
+  int8_t* row_w;
+  GemmGeom gv;          // the virtual geometry the pair kernel runs with
 };
 
 static void plan_free(i8ie_conv_plan* p) {
@@ -74,6 +78,7 @@ static void plan_free(i8ie_conv_plan* p) {
   if (p->border_tab) cudaFree(p->border_tab);
   if (p->stem_x) cudaFree(p->stem_x);
   if (p->stem_w) cudaFree(p->stem_w);
+  if (p->row_w) cudaFree(p->row_w);
   delete p;
 }
 
@@ -106,8 +111,40 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   p->border_tab = nullptr;
   p->stem_x = nullptr;
   p->stem_w = nullptr;
+  p->row_w = nullptr;
+  p->kr = 0;
   p->c = c;
   p->cluster = 1;
+  if (impl == 4) {
+    // row mode: x will be the physically padded tensor [n][h + 2p][w + 2p][cp]
+    if (tc_disabled() || !tc_row_mode_ok(c, kh, kw, stride, pad, out_cp) || cp != (c + 15) / 16 * 16) {
+      set_error("conv2d_plan_create: geometry not eligible for the row-mode kernel (c=%d cp=%d k=%dx%d s=%d p=%d out_cp=%d)",
+                c, cp, kh, kw, stride, pad, out_cp);
+      plan_free(p);
+      return nullptr;
+    }
+    p->impl = 4;
+    p->kr = tc_row_mode_kr(cp, kw);
+    p->gv = tc_row_mode_geom(g, p->kr);
+    p->bk = 128;
+    p->bn = tc_pick_bn_pair(p->gv, 128);
+    p->cluster = tc_conv_cluster(128, p->bn);
+    int rc4 = I8IE_OK;
+    if (p->cluster != 2) { set_error("conv2d_plan_create: row mode needs the pair kernel (bn=%d)", p->bn); rc4 = I8IE_EINVAL; }
+    if (rc4 == I8IE_OK && cudaMalloc(&p->row_w, (size_t)kc_pad * kh * p->kr) != cudaSuccess) {
+      set_error("conv2d_plan_create: cudaMalloc of the row-mode weights failed");
+      rc4 = I8IE_ECUDA;
+    }
+    if (rc4 == I8IE_OK) rc4 = tc_row_pack_weights(g, w_packed, p->row_w, p->kr, 0);
+    if (rc4 == I8IE_OK && cudaStreamSynchronize(0) != cudaSuccess) {
+      set_error("conv2d_plan_create: row-mode weight kernel failed");
+      rc4 = I8IE_ECUDA;
+    }
+    if (rc4 == I8IE_OK)
+      rc4 = tc_encode_weight_map(&p->tmB, p->row_w, kc_pad, kh * p->kr, 128, tc_pair_box_rows(p->bn));
+    if (rc4 != I8IE_OK) { plan_free(p); return nullptr; }
+    return p;
+  }
   const bool stem_ok = tc_stem_eligible(g, c) && !tc_disabled();
   const bool eligible = tc_conv_eligible(g) && !tc_disabled();
   if (impl == 2 && !eligible && !stem_ok) {
@@ -148,9 +185,9 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   }
   if (rc == I8IE_OK && p->impl == 2) {
     p->bk = tc_conv_bk(g);
-    p->bn = tc_pick_bn(g.out_cp);   // every lane of the padded output pitch is written
+    p->bn = tc_pick_bn_pair(g, p->bk);   // every lane of the padded output pitch is written
     p->cluster = tc_conv_cluster(p->bk, p->bn);
-    rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->cluster > 1 ? p->bn / 2 : p->bn);
+    rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->cluster > 1 ? tc_pair_box_rows(p->bn) : p->bn);
     const int tab = tc_border_table_size(g);
     if (rc == I8IE_OK && tab > 0) {
       if (cudaMalloc(&p->border_tab, sizeof(int32_t) * (size_t)tab) != cudaSuccess) {
@@ -176,6 +213,11 @@ void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan) { plan_free(plan); }
 
 int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan) { return plan ? plan->impl : 0; }
 
+int i8ie_conv2d_row_mode_cp(int c, int cp_plain, int kh, int kw, int stride, int pad, int out_cp) {
+  if (tc_disabled()) return 0;
+  return tc_row_mode_cp(c, cp_plain, kh, kw, stride, pad, out_cp);
+}
+
 int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int32_t* oc, float sa,
                    float sb, float sc, int zp_in, int zp_out, int flags, int32_t* acc_out, void* stream) {
   I8IE_REQUIRE(plan && x && y && oc, "conv2d_u8: null argument");
@@ -188,6 +230,13 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
     if (plan->stem2)
       return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
     return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+  }
+  if (plan->impl == 4) {   // x = physically padded input (border = zp_in): no border table, exact by construction
+    CUtensorMap tmA;
+    int rc = plan->amaps.get(x, 4, 0, 0, 0, &tmA,
+                             [&](CUtensorMap* m) { return tc_encode_act_map_row_mode(m, x, plan->g, plan->kr); });
+    if (rc != I8IE_OK) return rc;
+    return launch_tc_conv(plan->gv, tmA, plan->tmB, 128, plan->bn, 2, nullptr, y, ep, zp_in, (cudaStream_t)stream);
   }
   if (plan->impl == 2) {
     CUtensorMap tmA;

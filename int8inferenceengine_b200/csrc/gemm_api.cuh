@@ -36,7 +36,16 @@ int tc_build_border_table(const GemmGeom& g, const int8_t* w_packed, int32_t* ta
 int tc_encode_weight_map(CUtensorMap* tm, const int8_t* w, int rows, int ldw, int bk, int bn);
 int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int bk);
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx);
+// row mode: physically padded input, K = (filter row, byte of the kw * cp run) — see tc_gemm.cu
+int tc_row_mode_cp(int c, int cp_plain, int kh, int kw, int stride, int pad, int out_cp);
+bool tc_row_mode_ok(int c, int kh, int kw, int stride, int pad, int out_cp);
+int tc_row_mode_kr(int cpx, int kw);
+int tc_row_pack_weights(const GemmGeom& g, const int8_t* w_packed, int8_t* wr, int kr, cudaStream_t stream);
+int tc_encode_act_map_row_mode(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int kr);
+GemmGeom tc_row_mode_geom(const GemmGeom& g, int kr);
 int tc_conv_cluster(int bk, int bn);   // 2 = CTA-pair kernel (cta_group::2), 1 = single CTAs
+int tc_pair_box_rows(int bn);          // weight-map box rows of the pair kernel
+int tc_pick_bn_pair(const GemmGeom& g, int bk);   // cost-model N tile for conv plans (pair kernel candidates)
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream);
 void tc_fc_config(int m, int ldy, int k, int* bn, int* splits, int* kb_per);

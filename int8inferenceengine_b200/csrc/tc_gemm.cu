@@ -65,6 +65,11 @@ struct TcParams {
   int splits, kb_per;
   int32_t* ws;                // [splits][M][ws_ld]
   int ws_ld;
+  // fused split-K finish: every CTA owns exactly ONE (split, tile) and all of them are co-resident
+  // (cooperative launch). After dumping its partial tile a CTA announces it on sk_counters[2*mn],
+  // waits for its siblings, then folds + requantises ITS share of the tile's rows — no second kernel.
+  int fused_reduce;
+  unsigned* sk_counters;      // [tiles_m * tiles_n][2] = {arrived, finished}, zero between launches
   // 128-row sub-tiles per CTA tile (1 or 2): two accumulators share every weight stage, which
   // cuts the L2->SM bytes per MAC (the binding limit of a 128 x BN tile, ~43 B/clk/SM)
   int mt;
@@ -199,6 +204,83 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
       *reinterpret_cast<uint4*>(yrow + n0 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       if (n0 + c0 + 16 < p.out_cp)
         *reinterpret_cast<uint4*>(yrow + n0 + c0 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+}
+
+// Fused split-K finish (small-M fc, see TcParams::fused_reduce), run by the 8 epilogue warps of a CTA
+// right after they dumped the CTA's partial tile: release the partials (fence + barrier + one atomic
+// add on the tile's counter), wait until all `splits` sibling CTAs have done the same, then fold and
+// requantise the rows split, split + splits, ... of the tile: y = requant(sum_s ws[s] + oc (+ bias)).
+// Integer adds commute, so the result does not depend on the order (bit-exact, fully_connected.cc:39-48).
+template <int BN>
+__device__ __forceinline__ void splitk_fused_finish(const TcParams& p, int split, int mn, int m0, int n0, int et,
+                                                    float rcp) {
+  __threadfence();   // this thread's partial stores are visible at GPU scope before the arrival below
+  epi_bar_sync();
+  unsigned* cnt = p.sk_counters + 2 * mn;
+  if (et == 0) {
+    atomicAdd(cnt, 1u);
+    long long t0 = 0;
+    for (unsigned n = 0;; ++n) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+      if (v >= (unsigned)p.splits) break;
+      if ((n & 63u) == 63u) {
+        const long long t = clock64();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ll) { tc_fail(8); break; }
+      }
+    }
+  }
+  epi_bar_sync();   // (the acquire above + this barrier order every epilogue thread's reads after the siblings' stores)
+  const int rows = min(BM, p.M - m0);
+  const int quads = min(BN, p.out_cp - n0) >> 2;          // 4-channel groups of this N tile
+  const size_t split_stride = (size_t)p.M * p.ws_ld;
+  const float zpf = (float)p.ep.zp_out;
+  const uint32_t zlo = p.ep.relu ? (uint32_t)p.ep.zp_out : 0u;
+  // thread -> (row slot, channel quad): consecutive threads read consecutive 16-byte groups of one row
+  for (int idx = et; idx < ((rows - split + p.splits - 1) / p.splits) * quads; idx += 32 * kEpiWarps) {
+    const int r = split + (idx / quads) * p.splits, n4 = n0 + (idx % quads) * 4;
+    const int m = m0 + r;
+    const int32_t* src = p.ws + (size_t)m * p.ws_ld + n4;
+    int4 a = make_int4(0, 0, 0, 0);
+    int s = 0;
+    for (; s + 4 <= p.splits; s += 4) {
+      int4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const int4*>(src + (size_t)(s + j) * split_stride));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+    }
+    for (; s < p.splits; ++s) {
+      const int4 v = __ldcg(reinterpret_cast<const int4*>(src + (size_t)s * split_stride));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const int32_t acc[4] = {a.x, a.y, a.z, a.w};
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n4 + j;
+      uint32_t q = (uint32_t)p.ep.zp_out;   // pad lanes carry the zero point
+      if (n < p.N) {
+        int32_t v = acc[j] + __ldg(p.ep.oc + n);
+        if (p.ep.bias_f) v = fc_bias_add(v, __ldg(p.ep.bias_f + n));
+        if (p.ep.acc_out) p.ep.acc_out[(size_t)m * p.N + n] = v;
+        const uint32_t y = p.fast_requant ? requant_u8_fast(v, p.ep.sa, p.ep.sb, p.ep.sc, rcp, zpf)
+                                          : requant_u8(v, p.ep.sa, p.ep.sb, p.ep.sc, zpf);
+        q = max(y, zlo);
+      }
+      word |= q << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(p.y + (size_t)m * p.out_cp + n4) = word;
+  }
+  // the last CTA of the tile to finish re-arms the counters for the next launch
+  epi_bar_sync();
+  if (et == 0) {
+    if (atomicAdd(cnt + 1, 1u) == (unsigned)p.splits - 1u) {
+      cnt[0] = 0u; cnt[1] = 0u;
+      __threadfence();
     }
   }
 }
@@ -379,6 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
             }
           }
+          if (p.fused_reduce) splitk_fused_finish<BN>(p, split, mn, m0, n0, et, rcp);
         } else {
           // spatial border class of this output pixel -> row of the zero-point correction table
           const int32_t* corr = nullptr;
@@ -415,6 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
 // cluster work on ONE 256 x BN tile: each CTA loads its own 128 rows of A and only HALF of the
 // weight rows; tcgen05.mma.cta_group::2 (issued by the even CTA) reads both halves and fills both
 // CTAs' TMEM (rows 0-127 / 128-255). Per-SM operand traffic drops to (128 + BN/2) * BK.
+// BN = 384 (layers with 384 output channels): ONE A stage feeds two MMAs of N = 192 (columns 0-191 and
+// 192-383 of a single 384-column accumulator), so A is fetched once instead of once per 192-wide N tile:
+// 40 KB per 768 tensor clocks (52 B/clk/SM) instead of 28 KB per 384 (73 B/clk/SM) against the measured
+// 46.6 B/clk/SM L2 -> SM ingest (profiles/i8_peak.json). TMEM then holds one accumulator, so the epilogue
+// of a tile no longer overlaps the next tile's MMAs — the host picks BN per plan from a cost model.
 //   full[s]       even CTA only, 1 arrival (its producer, expecting the bytes of BOTH CTAs)
 //   empty[s]      each CTA, 1 arrival (the even CTA's multicast commit)
 //   tmem_full[b]  each CTA, 1 arrival (multicast commit)
@@ -427,7 +515,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int BK = 128;
-  constexpr int kSubA = BM * BK, kSubBh = (BN / 2) * BK;
+  constexpr int NSPLIT = BN > 256 ? 2 : 1;     // MMAs per K step (UMMA N <= 256)
+  constexpr int BNI = BN / NSPLIT;             // N of one MMA instruction
+  constexpr int kSubA = BM * BK, kSubBq = (BNI / 2) * BK, kSubBh = NSPLIT * kSubBq;
   constexpr int kStage = kSubA + kSubBh;
   constexpr uint32_t NACC = num_acc<BN>();
   TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
@@ -478,14 +568,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
           uint8_t* sa = smem + (size_t)s * kStage;
           ptx::tma_load_im2col_4d_2cta(sa, &tmA, &ctl->full[s], cb * BK, bw, bh, bimg, (uint16_t)kx, (uint16_t)ky);
           if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
-          ptx::tma_load_2d_2cta(sa + kSubA, &tmB, &ctl->full[s], kb * BK, n0 + crank * (BN / 2));
+#pragma unroll
+          for (int h = 0; h < NSPLIT; ++h)   // this CTA's half of the weight rows of every N = BNI instruction
+            ptx::tma_load_2d_2cta(sa + kSubA + h * kSubBq, &tmB, &ctl->full[s], kb * BK, n0 + h * BNI + crank * (BNI / 2));
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the even CTA drives the tensor cores of both SMs =====
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = ptx::make_idesc_i8(2 * BM, BN);
+      constexpr uint32_t idesc = ptx::make_idesc_i8(2 * BM, BNI);
       const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
       uint32_t it = 0, acc_it = 0;
       bool alive = true;
@@ -504,8 +596,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
           const uint32_t a_lo = ptx::smem_desc_lo(sa), b_lo = ptx::smem_desc_lo(sa + kSubA);
 #pragma unroll
           for (int k = 0; k < BK / 32; ++k) {
-            ptx::mma_i8_ss_lohi_2cta(d_tmem, a_lo + (uint32_t)((k * 32) >> 4), desc_hi, b_lo + (uint32_t)((k * 32) >> 4),
-                                     desc_hi, idesc, accf);
+#pragma unroll
+            for (int h = 0; h < NSPLIT; ++h)
+              ptx::mma_i8_ss_lohi_2cta(d_tmem + (uint32_t)(h * BNI), a_lo + (uint32_t)((k * 32) >> 4), desc_hi,
+                                       b_lo + (uint32_t)((h * kSubBq + k * 32) >> 4), desc_hi, idesc, accf);
             accf = 1;
           }
           ptx::tc_commit_2cta_multicast(&ctl->empty[s], 3);   // both CTAs' slots are free once these MMAs have read them
@@ -1043,6 +1137,26 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
   if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
 }
 
+// ---- row mode (stride-1 convs whose channel count is not a multiple of 128) ----------------------
+// With the input stored PHYSICALLY padded as [n][h + 2p][w + 2p][cpx] (border = zero point), the kw taps of
+// one filter row of one output pixel are ONE contiguous run of kw * cpx bytes. The GEMM K index becomes
+// (filter row, byte of the run) with the run rounded up to KR = a multiple of 128 bytes (the tail reads the
+// neighbouring pixel against zero weights), instead of (tap, channel) with every tap padded to 128 channels:
+// AlexNet conv2 (C = 96, 5 x 5) runs 5 x 512 = 2560 bytes of K per pixel instead of 25 x 128 = 3200, and needs no
+// zero-point border table (the padding is real, exactly conv2d.cc:24-25). The kernel is unchanged: the TMA
+// im2col map describes a virtual tensor {KR "channels", ow positions at a pitch of cpx bytes, h + 2p rows, n}
+// with a kh x 1 filter — overlapping "pixels", as in the stem view.
+// Weights: wr[n][r][KR], byte (x * cpx + ch) of row r = w_packed[n][r][x][ch], zero beyond kw * cpx.
+__global__ void row_weight_kernel(const int8_t* __restrict__ wp, int8_t* __restrict__ wr, int kc_pad, int kh, int kw,
+                                  int cp, int kr) {
+  const int64_t total = (int64_t)kc_pad * kh * kr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i % kr);
+    const int64_t nr = i / kr;   // n * kh + r
+    wr[i] = b < kw * cp ? wp[nr * kw * cp + b] : (int8_t)0;
+  }
+}
+
 // zero-point border correction table: tab[cls][n] = sum over spatially out-of-range taps of
 // the packed weight, cls = ((th*(pad+1)+bh)*(pad+1)+tw)*(pad+1)+bw  (rows [0,th) and
 // [kh-bh,kh), cols [0,tw) and [kw-bw,kw) are out of range).
@@ -1169,6 +1283,9 @@ __global__ void __launch_bounds__(256) fc_splitk_reduce_kernel(const int32_t* __
 std::mutex g_ws_mu;
 int32_t* g_ws = nullptr;
 size_t g_ws_bytes = 0;
+// the last kSkCounterBytes of the scratch allocation hold the fused split-K counters (zero whenever no
+// fc kernel is running: the kernels re-arm them)
+constexpr int kSkCounterBytes = 4096;
 
 int ensure_workspace(size_t bytes, cudaStream_t stream, int32_t** out) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
@@ -1180,8 +1297,9 @@ int ensure_workspace(size_t bytes, cudaStream_t stream, int32_t** out) {
     I8IE_CUDA_OK(cudaDeviceSynchronize());
     if (g_ws) cudaFree(g_ws);
     g_ws = nullptr; g_ws_bytes = 0;
-    const size_t want = bytes + (bytes >> 2);
+    const size_t want = ((bytes + (bytes >> 2)) + 255) & ~size_t(255);
     I8IE_CUDA_OK(cudaMalloc(&g_ws, want));
+    I8IE_CUDA_OK(cudaMemset(reinterpret_cast<uint8_t*>(g_ws) + want - kSkCounterBytes, 0, kSkCounterBytes));
     g_ws_bytes = want;
   }
   *out = g_ws;
@@ -1253,6 +1371,23 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (p.fused_reduce) {
+    // the sibling CTAs of a tile wait for one another: all of them must be resident at once
+    I8IE_REQUIRE(tiles == grid, "tcgen05 fc: fused split-K needs one tile per CTA (%d tiles, %d SMs)", tiles, num_sms());
+    // Co-residency: one CTA per SM (shared memory) and grid <= SM count, so on a stream that has the GPU to
+    // itself every CTA is resident. I8IE_FC_COOP=1 asks the driver to guarantee it (cooperative launch:
+    // measured ~3 us slower per launch on B200, hence opt-in); a CTA that never sees its siblings times out
+    // and reports role 8 instead of hanging.
+    static const bool coop = std::getenv("I8IE_FC_COOP") != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    return check_launch("tc_igemm_kernel (fused split-K)");
+  }
   launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
@@ -1324,7 +1459,7 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, c
   const int kStage = BM * 128 + (BN / 2) * 128;
   int stages = (kMaxSmem - 1024 - ctl_bytes) / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
-  I8IE_REQUIRE(stages >= 2, "tcgen05 pair: no room for a pipeline");
+  I8IE_REQUIRE(stages >= 3, "tcgen05 pair: no room for a pipeline");
   p.stages = stages;
   const int smem = stages * kStage + ctl_bytes + 1024;
   p.mt = 1; p.splits = 1; p.kb_per = p.num_kb;
@@ -1406,6 +1541,58 @@ int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& 
   return encode_im2col_4d(tm, x, g, bk);
 }
 
+// ---- row mode host side (see row_weight_kernel) ----
+int tc_row_mode_kr(int cpx, int kw) { return (kw * cpx + 127) / 128 * 128; }
+
+// Hard constraints of row mode: stride 1, the pair kernel's wide N tiles, a run that fits a few K blocks.
+bool tc_row_mode_ok(int c, int kh, int kw, int stride, int pad, int out_cp) {
+  if (std::getenv("I8IE_NO_CLUSTER") != nullptr) return false;
+  if (stride != 1 || kw < 2 || pad > 8 || out_cp < 128 || kh > 16) return false;
+  return tc_row_mode_kr((c + 15) / 16 * 16, kw) <= 2048;
+}
+
+// Channel pitch (bytes per pixel) the physically padded input must have, or 0 when the layer should
+// stay on the plain im2col path (auto dispatch): row mode must save at least 10 % of the K bytes.
+int tc_row_mode_cp(int c, int cp_plain, int kh, int kw, int stride, int pad, int out_cp) {
+  if (std::getenv("I8IE_NO_ROW_MODE") != nullptr || !tc_row_mode_ok(c, kh, kw, stride, pad, out_cp)) return 0;
+  const int cpx = (c + 15) / 16 * 16;
+  const long long k_plain = (long long)kh * kw * cp_plain;
+  return (long long)kh * tc_row_mode_kr(cpx, kw) * 10 <= k_plain * 9 ? cpx : 0;
+}
+
+int tc_row_pack_weights(const GemmGeom& g, const int8_t* w_packed, int8_t* wr, int kr, cudaStream_t stream) {
+  const int64_t total = (int64_t)g.n_pad * g.kh * kr;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  row_weight_kernel<<<blocks, 256, 0, stream>>>(w_packed, wr, g.n_pad, g.kh, g.kw, g.cp, kr);
+  return check_launch("row_weight_kernel");
+}
+
+// x = padded input [n][h + 2p][w + 2p][cp] (g is the layer's REAL geometry with cp = the padded tensor's pitch)
+int tc_encode_act_map_row_mode(CUtensorMap* tm, const uint8_t* x, const GemmGeom& g, int kr) {
+  static EncodeIm2colFn fn = driver_fn<EncodeIm2colFn>("cuTensorMapEncodeIm2col");
+  I8IE_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col entry point not available");
+  const int hp = g.h + 2 * g.pad, wp = g.w + 2 * g.pad;
+  cuuint64_t dims[4] = {(cuuint64_t)kr, (cuuint64_t)g.ow, (cuuint64_t)hp, (cuuint64_t)g.n};
+  cuuint64_t strides[3] = {(cuuint64_t)g.cp, (cuuint64_t)wp * g.cp, (cuuint64_t)hp * wp * g.cp};
+  int lower[2] = {0, 0};
+  int upper[2] = {0, -(g.kh - 1)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(x), dims, strides, lower, upper, 128,
+                  (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  I8IE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col (row-mode view) failed (%d): kr=%d ow=%d hp=%d n=%d cp=%d", (int)r,
+               kr, g.ow, hp, g.n, g.cp);
+  return I8IE_OK;
+}
+
+// The virtual geometry the pair kernel runs a row-mode layer with: kh x 1 filter over KR "channels".
+GemmGeom tc_row_mode_geom(const GemmGeom& g, int kr) {
+  GemmGeom v = g;
+  v.h = g.h + 2 * g.pad; v.w = g.ow; v.cp = kr;
+  v.kw = 1; v.pad = 0; v.ldw = g.kh * kr;
+  return v;
+}
+
 int tc_encode_act_map_rows(CUtensorMap* tm, const uint8_t* x, int m, int k, int ldx) {
   return encode_tiled_2d(tm, x, (uint64_t)k, (uint64_t)m, (uint64_t)ldx, 128, BM);
 }
@@ -1417,8 +1604,41 @@ int tc_pick_bn(int n) { return pick_bn(n); }
 // then holds bn / 2 rows = whole 1 KB swizzle atoms). I8IE_NO_CLUSTER=1 forces single CTAs (tests).
 int tc_conv_cluster(int bk, int bn) {
   if (std::getenv("I8IE_NO_CLUSTER") != nullptr) return 1;
-  const bool ok = bk == 128 && (bn == 256 || bn == 192 || bn == 128) && ((bn / 2) * bk) % 1024 == 0;
+  const bool ok = bk == 128 && (bn == 384 || bn == 256 || bn == 192 || bn == 128);
   return ok ? 2 : 1;
+}
+
+// Rows of the weight tensor map's box for the pair kernel: each CTA loads its half of the rows of every
+// MMA instruction (N <= 256 per instruction; BN = 384 is two instructions of N = 192).
+int tc_pair_box_rows(int bn) { return bn > 256 ? bn / 4 : bn / 2; }
+
+// N tile of a conv plan served by the pair kernel. Cost model per candidate (clocks, one SM pair):
+//   tile  = K blocks x max(tensor clocks, L2 ingest clocks)      tensor: 2 * BN per 128-byte K block;
+//           ingest: (16 KB of A + 64 * BN bytes of weights) at ~40 B/clk/SM (85 % of the measured 46.6)
+//   total = waves over the 74 SM pairs x tile  (+ the exposed epilogue of the single-accumulator BN = 384
+//           variant for every further tile of a pair)
+// The widest tile wins when the work is a single wave (batch 100: conv3/conv4 in one wave of 256 x 384 tiles
+// instead of two waves of 256 x 192); at other batch sizes wave quantisation decides.
+int tc_pick_bn_pair(const GemmGeom& g, int bk) {
+  const int base = pick_bn(g.out_cp);
+  if (const char* e = std::getenv("I8IE_TC_BN"))   // dev / test override (384 only where it tiles the channels)
+    return (std::atoi(e) == 384 && bk == 128 && g.out_cp % 384 == 0 && std::getenv("I8IE_NO_CLUSTER") == nullptr) ? 384 : base;
+  if (bk != 128 || std::getenv("I8IE_NO_CLUSTER") != nullptr) return base;
+  const int pairs = std::max(1, num_sms() / 2);
+  const long long num_kb = (long long)g.kh * g.kw * (g.cp / 128);
+  const long long tiles_m = ((g.M + BM - 1) / BM + 1) / 2;
+  int best = base;
+  long long best_cost = -1;
+  for (int bn : {384, 256, 192, 128}) {
+    if (bn > 256 && g.out_cp % bn != 0) continue;        // 384 only when it tiles the channels exactly
+    if (bn > g.out_cp && bn != base) continue;
+    const long long tiles = tiles_m * ((g.out_cp + bn - 1) / bn);
+    const long long waves = (tiles + pairs - 1) / pairs;
+    const long long tile = num_kb * std::max<long long>(2 * bn, (16384 + 64 * bn) / 40);
+    const long long cost = waves * tile + (bn > 256 ? (waves - 1) * (bn / 64) * 350 : 0);
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
@@ -1437,6 +1657,7 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
       case 128: return launch_pair_bn<128>(tmA, tmB, p, stream);
       case 192: return launch_pair_bn<192>(tmA, tmB, p, stream);
       case 256: return launch_pair_bn<256>(tmA, tmB, p, stream);
+      case 384: return launch_pair_bn<384>(tmA, tmB, p, stream);
     }
     set_error("tcgen05 pair: unsupported BN %d", bn);
     return I8IE_EINVAL;
@@ -1486,8 +1707,17 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   // split K across CTAs, then fold the partial sums (exact: integer adds commute)
   p.splits = splits; p.kb_per = kb_per;
   p.ws_ld = ((ldy + bn - 1) / bn) * bn;
-  int rc = ensure_workspace(sizeof(int32_t) * (size_t)p.splits * m * p.ws_ld, stream, &p.ws);
+  const int mn_tiles = ((m + BM - 1) / BM) * ((ldy + bn - 1) / bn);
+  const size_t part_bytes = (sizeof(int32_t) * (size_t)p.splits * m * p.ws_ld + 255) & ~size_t(255);
+  int rc = ensure_workspace(part_bytes + kSkCounterBytes, stream, &p.ws);
   if (rc != I8IE_OK) return rc;
+  // one kernel when every (split, tile) gets its own co-resident CTA; I8IE_FC_FUSED=0 keeps the two-kernel path
+  static const bool fused_ok = [] { const char* e = std::getenv("I8IE_FC_FUSED"); return !(e && e[0] == '0'); }();
+  if (fused_ok && mn_tiles * p.splits <= num_sms() && 2 * mn_tiles * (int)sizeof(unsigned) <= kSkCounterBytes) {
+    p.fused_reduce = 1;
+    p.sk_counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(g_ws) + g_ws_bytes - kSkCounterBytes);
+    return launch_bk<0>(128, bn, tmA, tmB, p, stream);
+  }
   rc = launch_bk<0>(128, bn, tmA, tmB, p, stream);
   if (rc != I8IE_OK) return rc;
   const long long threads = (long long)m * (ldy / 4);

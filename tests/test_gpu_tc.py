@@ -18,7 +18,26 @@ def _no_tc_error():
 
 
 FC = [(128, 32, 32), (128, 128, 32), (1, 64, 16), (100, 784, 10), (100, 7680, 10), (128, 9216, 256),
-      (300, 1000, 200), (130, 4096, 4096), (1000, 4096, 10), (257, 515, 129), (17, 33, 700)]
+      (300, 1000, 200), (130, 4096, 4096), (1000, 4096, 10), (257, 515, 129), (17, 33, 700),
+      # AlexNet fc1 / fc2 at the bench batch and at small batch: split-K across co-resident CTAs with the
+      # fold + requantise fused into the same kernel (sibling CTAs wait for one another's partial tiles)
+      (100, 9216, 4096), (100, 4096, 4096), (125, 9216, 4096), (7, 4096, 4096), (1, 9216, 4096), (33, 2000, 1000)]
+
+
+@pytest.mark.parametrize("shape", [(100, 9216, 4096), (16, 4096, 4096), (33, 2000, 1000)])
+def test_tc_fc_two_kernel_split_k(shape, monkeypatch):
+    """The two-kernel split-K path (partials + fc_splitk_reduce_kernel), used when the (split, tile) grid
+    does not fit the SMs; forced here with I8IE_FC_FUSED=0 in a fresh process-independent way."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent(f"""
+        import sys; sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r})
+        import test_gpu_tc as t
+        t.test_tc_fc({shape!r})
+    """)
+    env = dict(os.environ, I8IE_FC_FUSED="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stderr[-3000:]
 
 
 @pytest.mark.parametrize("shape", FC)
@@ -37,6 +56,10 @@ def test_tc_fc(shape):
     out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
     _no_tc_error()
     assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    for _ in range(3):   # back-to-back launches: the fused split-K counters re-arm themselves
+        out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=2)
+    _no_tc_error()
     assert np.array_equal(out.numpy(), exp)
     # pad lanes of the padded output rows carry the zero point
     ldy = (n + 15) // 16 * 16
@@ -87,7 +110,7 @@ PAIR = [  # shapes served by the CTA-pair kernel (cp % 128 == 0, N tile 128 / 19
 ]
 
 
-def _run_conv_parity(geom):
+def _run_conv_parity(geom, impl=2):
     n, c, h, w_, kc, k, s, p = geom
     rng = np.random.default_rng(sum(geom) + 1)
     a = np.sqrt(6.0 / (c * k * k))
@@ -101,14 +124,15 @@ def _run_conv_parity(geom):
     exp, exp_acc = port.conv2d_u8(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
     oh, ow = exp.shape[2], exp.shape[3]
     acc = torch.empty(n * oh * ow * kc, dtype=torch.int32, device="cuda")
-    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=impl)
     _no_tc_error()
+    assert L._last_impl == impl
     assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
     assert np.array_equal(out.numpy(), exp)
     raw = out.buf.cpu().numpy().reshape(n * oh * ow, -1)
     assert np.all(raw[:, kc:] == out_zp)          # pad lanes of the output pitch carry the zero point
     L.fuse_relu = True
-    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=2)
+    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=impl)
     assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
 
 
@@ -139,6 +163,57 @@ PAIR_WRAP = [  # more pair tiles than the 74 clusters of the persistent grid, od
 @pytest.mark.parametrize("geom", PAIR_WRAP)
 def test_tc_conv_cta_pair_many_tiles(geom):
     _run_conv_parity(geom)
+
+
+@pytest.mark.parametrize("bn", ["128", "192", "256", "384"])
+@pytest.mark.parametrize("geom", [(100, 256, 13, 13, 384, 3, 1, 1),     # AlexNet conv3 at the bench batch (67 pair tiles)
+                                  (130, 384, 13, 13, 384, 3, 1, 1),     # conv4, 86 pair tiles: the accumulator is reused
+                                  (3, 128, 9, 9, 768, 3, 1, 1)])        # two 384-wide N tiles
+def test_tc_conv_pair_every_n_tile_width(geom, bn, monkeypatch):
+    """The pair kernel's N tile is picked by a cost model; every width it can pick (incl. the 384-column tile:
+    two N = 192 MMAs per K step on one A stage, single TMEM accumulator) stays bit-exact."""
+    monkeypatch.setenv("I8IE_TC_BN", bn)
+    _run_conv_parity(geom)
+
+
+ROW = [  # stride-1 convs whose channel count is not a multiple of 128: row mode (physically padded input,
+    # K = filter row x contiguous kw * cp run): n, c, h, w, kc, k, stride, pad
+    (9, 96, 27, 27, 256, 5, 1, 2),       # AlexNet conv2: 5 x 512 bytes of K instead of 25 x 128
+    (40, 96, 27, 27, 256, 5, 1, 2),      # ... with more pair tiles than clusters
+    (3, 48, 14, 14, 128, 3, 1, 1),       # run of 144 bytes -> KR 256
+    (2, 160, 9, 9, 256, 3, 1, 0),        # no padding, run 480 -> 512
+    (5, 20, 28, 28, 130, 5, 1, 3),       # pad 3, C = 20 -> pitch 32, run 160 -> 256, ragged N
+    (2, 200, 11, 7, 384, 2, 1, 1),       # even filter, non-square image, N = 384
+]
+
+
+@pytest.mark.parametrize("geom", ROW)
+def test_tc_conv_row_mode(geom):
+    _run_conv_parity(geom, impl=4)
+
+
+def test_row_mode_is_auto_selected_and_fed_by_the_pool():
+    """Auto dispatch takes row mode for AlexNet conv2, and a pending max-pool writes the physically padded
+    operand directly (no NHWC round trip): pool -> conv equals the oracle's pool -> conv."""
+    from int8inferenceengine_b200 import backend as B
+    rng = np.random.default_rng(5)
+    n, c, h, w_ = 6, 96, 55, 55
+    q = rng.integers(0, 256, size=(n, c, h, w_), dtype=np.uint8)
+    a = np.sqrt(6.0 / (c * 25))
+    w = rng.uniform(-a, a, size=(256, c, 5, 5)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(256,)).astype(np.float32)
+    in_scale, in_zp, out_scale, out_zp = np.float32(0.0518), 116, np.float32(0.0819), 105
+    L = make_layer("conv", w, b, (out_scale, out_zp), 1, 2)
+    x = u8_tensor_from_nchw(q, in_scale, in_zp)
+    pooled = B.max_pool2d(x, 3, 2)
+    y = L(pooled)
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp = port.conv2d_u8(port.max_pool2d_u8(q, 3, 2), qw, qb, 1, 2, in_scale, in_zp, ws, out_scale, out_zp)
+    assert np.array_equal(y.numpy(), exp)
+    _no_tc_error()
+    assert L._last_impl == 4
+    assert pooled._pending("pool") is not None      # the pool itself was never launched in its NHWC form
+    assert np.array_equal(pooled.numpy(), port.max_pool2d_u8(q, 3, 2))
 
 
 def test_tc_ineligible_shapes_are_refused_when_forced():
