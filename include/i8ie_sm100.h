@@ -231,6 +231,15 @@ I8IE_API int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, 
                    float sa, float sb, float sc, int zp_in, int zp_out, int flags,
                    int32_t* acc_out, void* stream);
 
+/* F4 extension (opt-in; NOT in the reference, whose weight scale is one per tensor, layer.cc:18-19):
+ * per-output-channel weight scales. sb_vec = device float[kc] that must outlive the plan's use;
+ * [sb_min, sb_max] bound its entries (the exact fast requantise path is guarded on both). Every later
+ * i8ie_conv2d_u8 / i8ie_conv2d_f32_u8 call of the plan requantises channel n with
+ *   d = ((float)acc * sa) * sb_vec[n]   (otherwise quantize_utils.cc:27-36 unchanged)
+ * and ignores its scalar `sb`. sb_vec = NULL restores the per-tensor behaviour. */
+I8IE_API int i8ie_conv2d_plan_set_channel_scales(i8ie_conv_plan* plan, const float* sb_vec, float sb_min,
+                                                 float sb_max);
+
 /* Module.__call__'s input quantise (i8ie/module.py:20 -> quantize_utils.cc:44-52) fused into
  * the first convolution: x is the fp32 NCHW image; q = (u8)(x/in_scale + in_zp) is produced
  * on the fly into the plan's stem buffer and never stored as an NHWC tensor. Only valid
@@ -251,6 +260,12 @@ I8IE_API int i8ie_conv2d_f32_u8_indirect(i8ie_conv_plan* plan, const float* cons
 I8IE_API int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
                int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
                float sc, int zp_out, int flags, int32_t* acc_out, int impl, void* stream);
+/* i8ie_fc_u8 with per-output-channel weight scales (F4 extension, see
+ * i8ie_conv2d_plan_set_channel_scales): sb_vec = device float[n], bounded by [sb_min, sb_max]. */
+I8IE_API int i8ie_fc_u8_pc(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+                           int m, int n, int k, const int32_t* oc, const float* bias_f, float sa,
+                           const float* sb_vec, float sb_min, float sb_max, float sc, int zp_out, int flags,
+                           int32_t* acc_out, int impl, void* stream);
 
 /* Debug hook (not part of the reference-facing surface): synchronises the device and
  * returns the first protocol error (mbarrier wait timeout) a tensor-core kernel recorded

@@ -748,6 +748,12 @@ class Calibrator:
 # ---- layers (include/layer.h, src/layer.cc, conv2d.cc, fully_connected.cc) ----------------
 
 class _BaseLayer:
+    # F4 extension (opt-in, not in the reference): set `layer.per_channel = True` before convert() to
+    # quantise every output channel's weights (and its bias entry) with its own scale — layer.cc:6-26
+    # applied per channel — and requantise with that channel's scale. The default (False) is the
+    # reference's single per-tensor scale and stays bit-identical to it.
+    per_channel = False
+
     def __init__(self, weight_shape, out_channel):
         _need_cuda()
         # BaseLayer ctor allocates uninitialised weight/bias (layer.h:9-12)
@@ -825,8 +831,26 @@ class _BaseLayer:
         qw = np.empty(self._w.shape, np.int8)
         qb = np.empty(self._b.shape, np.int8)
         sc = C.c_float()
-        check(L.i8ie_quantize_weight_host(self._w.ctypes.data, self._w.size, self._b.ctypes.data, self._b.size,
-                                          qw.ctypes.data, qb.ctypes.data, C.byref(sc)), "quantize_weight_host")
+        self._w_scales = None
+        self._w_scales_dev = None
+        if self.per_channel:
+            n = self._w.shape[0]
+            per = self._w.size // n
+            scales = np.empty(n, np.float32)
+            w2, qw2 = self._w.reshape(n, per), qw.reshape(n, per)
+            for j in range(n):
+                check(L.i8ie_quantize_weight_host(w2[j].ctypes.data, per, self._b[j:j + 1].ctypes.data, 1,
+                                                  qw2[j].ctypes.data, qb[j:j + 1].ctypes.data, C.byref(sc)),
+                      "quantize_weight_host")
+                scales[j] = sc.value
+            if not np.all(np.isfinite(scales)) or scales.min() <= 0:
+                raise I8ieError("per_channel: a channel's weights and bias are all equal (zero scale)")
+            self._w_scales = scales
+            self._w_scales_dev = torch.from_numpy(scales).cuda()
+            sc.value = float(scales.max())
+        else:
+            check(L.i8ie_quantize_weight_host(self._w.ctypes.data, self._w.size, self._b.ctypes.data, self._b.size,
+                                              qw.ctypes.data, qb.ctypes.data, C.byref(sc)), "quantize_weight_host")
         self._w_scale = np.float32(sc.value)
         self._qw_dev = torch.from_numpy(qw.reshape(qw.shape[0], -1)).cuda()
         self._qb_dev = torch.from_numpy(qb).cuda()
@@ -846,6 +870,10 @@ class _BaseLayer:
 
     def q_bias(self):
         return TensorS8(_Storage(self._qb_dev), [self._qb_dev.numel()], scale=self._w_scale)
+
+    def weight_scales(self):
+        """Per-output-channel weight scales (numpy f32 [n]) of a layer converted with per_channel = True, else None."""
+        return None if getattr(self, "_w_scales", None) is None else self._w_scales.copy()
 
     def _offsets(self, in_zp, in_scale, is_conv):
         key = (int(in_zp), float(in_scale))
@@ -933,10 +961,17 @@ class Linear(_BaseLayer):
         ldy = _r16(n)
         out = torch.empty(m * ldy, dtype=torch.uint8, device=buf.device)
         flags = 1 if (self.fuse_relu if relu is None else relu) else 0
-        check(L.i8ie_fc_u8(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
-                           out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
-                           float(self._w_scale), float(self._scale), self._zp, flags,
-                           acc_out.data_ptr() if acc_out is not None else None, impl, _stream()), "fc_u8")
+        if getattr(self, "_w_scales_dev", None) is not None:
+            check(L.i8ie_fc_u8_pc(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
+                                  out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
+                                  self._w_scales_dev.data_ptr(), float(self._w_scales.min()), float(self._w_scales.max()),
+                                  float(self._scale), self._zp, flags,
+                                  acc_out.data_ptr() if acc_out is not None else None, impl, _stream()), "fc_u8_pc")
+        else:
+            check(L.i8ie_fc_u8(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
+                               out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
+                               float(self._w_scale), float(self._scale), self._zp, flags,
+                               acc_out.data_ptr() if acc_out is not None else None, impl, _stream()), "fc_u8")
         return _new_u8_nhwc(out, m, n, 1, 1, ldy, self._scale, self._zp, two_d=True)
 
 
@@ -998,6 +1033,9 @@ class Conv2d(_BaseLayer):
                                           self._packed_for(cp).data_ptr(), self._kc_pad, impl)
             if not p:
                 raise I8ieError(f"conv2d_plan_create failed: {_lib.last_error()}")
+            if getattr(self, "_w_scales_dev", None) is not None:
+                check(L.i8ie_conv2d_plan_set_channel_scales(p, self._w_scales_dev.data_ptr(), float(self._w_scales.min()),
+                                                            float(self._w_scales.max())), "conv2d_plan_set_channel_scales")
             self._plans[key] = p
         return p
 

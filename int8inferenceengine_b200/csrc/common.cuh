@@ -184,6 +184,22 @@ __device__ __forceinline__ void requant2_u8_fast(int32_t a0, int32_t a1, const R
   y1 = f32_to_u8_sat_rz(r1);
 }
 
+// Same with the weight scale given per element pair (per-output-channel scales, F4 extension).
+template <bool RELU>
+__device__ __forceinline__ void requant2_u8_fast_sb(int32_t a0, int32_t a1, const RequantFast2& c, f32x2_t sb2,
+                                                    uint32_t& y0, uint32_t& y1) {
+  f32x2_t d = f2_pack(__int2float_rn(a0), __int2float_rn(a1));
+  d = f2_mul(f2_mul(d, c.sa), sb2);
+  const f32x2_t q0 = f2_mul(d, c.rcp);
+  const f32x2_t e = f2_fma(c.nsc, q0, d);
+  const f32x2_t q = f2_fma(e, c.rcp, q0);
+  float r0, r1;
+  f2_unpack(f2_add(q, c.zp), r0, r1);
+  if (RELU) { r0 = fmaxf(r0, c.zpf); r1 = fmaxf(r1, c.zpf); }
+  y0 = f32_to_u8_sat_rz(r0);
+  y1 = f32_to_u8_sat_rz(r1);
+}
+
 // FC's `C[i*n+j] += q_bias[j] / in.scale()` (fully_connected.cc:44): int += float.
 __device__ __forceinline__ int32_t fc_bias_add(int32_t acc, float bias_f) {
   return __float2int_rz(__fadd_rn(__int2float_rn(acc), bias_f));
@@ -337,6 +353,17 @@ struct EpiParams {
   int zp_out;             // out zero point
   int relu;               // fuse relu<u8>
   int32_t* acc_out;       // optional [m, n] s32 dump (parity tests)
+  // F4 extension (opt-in, not in the reference): per-output-channel weight scales. sb_vec = device [n]
+  // (then `sb` is ignored and [sb_min, sb_max] bounds its entries for the fast-path guard); nullptr = the
+  // reference's single per-tensor scale (layer.cc:18-19).
+  const float* sb_vec = nullptr;
+  float sb_min = 0.f, sb_max = 0.f;
 };
+
+// requant_fast_ok for an epilogue with either kind of weight scale
+inline bool requant_fast_ok(const EpiParams& ep) {
+  if (ep.sb_vec == nullptr) return requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  return requant_fast_ok(ep.sa, ep.sb_min, ep.sc) && requant_fast_ok(ep.sa, ep.sb_max, ep.sc);
+}
 
 }  // namespace i8ie

@@ -71,7 +71,14 @@ struct i8ie_conv_plan {
   int kr;
   int8_t* row_w;
   GemmGeom gv;          // the virtual geometry the pair kernel runs with
+  // F4 extension: per-output-channel weight scales (device [kc], owned by the caller) or nullptr
+  const float* sb_vec;
+  float sb_min, sb_max;
 };
+
+static void apply_channel_scales(const i8ie_conv_plan* plan, EpiParams* ep) {
+  if (plan->sb_vec != nullptr) { ep->sb_vec = plan->sb_vec; ep->sb_min = plan->sb_min; ep->sb_max = plan->sb_max; }
+}
 
 static void plan_free(i8ie_conv_plan* p) {
   if (!p) return;
@@ -113,6 +120,8 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   p->stem_w = nullptr;
   p->row_w = nullptr;
   p->kr = 0;
+  p->sb_vec = nullptr;
+  p->sb_min = p->sb_max = 0.f;
   p->c = c;
   p->cluster = 1;
   if (impl == 4) {
@@ -213,6 +222,15 @@ void i8ie_conv2d_plan_destroy(i8ie_conv_plan* plan) { plan_free(plan); }
 
 int i8ie_conv2d_plan_impl(const i8ie_conv_plan* plan) { return plan ? plan->impl : 0; }
 
+int i8ie_conv2d_plan_set_channel_scales(i8ie_conv_plan* plan, const float* sb_vec, float sb_min, float sb_max) {
+  I8IE_REQUIRE(plan != nullptr, "conv2d_plan_set_channel_scales: null plan");
+  I8IE_REQUIRE(sb_vec == nullptr || (sb_min > 0.f && sb_max >= sb_min), "conv2d_plan_set_channel_scales: bad bounds");
+  plan->sb_vec = sb_vec;
+  plan->sb_min = sb_min;
+  plan->sb_max = sb_max;
+  return I8IE_OK;
+}
+
 int i8ie_conv2d_row_mode_cp(int c, int cp_plain, int kh, int kw, int stride, int pad, int out_cp) {
   if (tc_disabled()) return 0;
   return tc_row_mode_cp(c, cp_plain, kh, kw, stride, pad, out_cp);
@@ -223,6 +241,7 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
   I8IE_REQUIRE(plan && x && y && oc, "conv2d_u8: null argument");
   I8IE_REQUIRE(zp_in >= 0 && zp_in <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_u8: zero point out of range");
   EpiParams ep{oc, nullptr, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  apply_channel_scales(plan, &ep);
   tc_error_sink_touch((cudaStream_t)stream);
   if (plan->impl == 3) {
     int rc = tc_stem_pack_input(plan->g, plan->stem, x, plan->stem_x, zp_in, (cudaStream_t)stream);
@@ -256,6 +275,7 @@ static int conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, const float*
   I8IE_REQUIRE(plan->impl == 3, "conv2d_f32_u8: only stem plans fuse the input quantise (plan impl=%d)", plan->impl);
   I8IE_REQUIRE(in_zp >= 0 && in_zp <= 255 && zp_out >= 0 && zp_out <= 255, "conv2d_f32_u8: zero point out of range");
   EpiParams ep{oc, nullptr, in_scale, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  apply_channel_scales(plan, &ep);
   tc_error_sink_touch((cudaStream_t)stream);
   if (plan->stem2 && tc_stem2_can_fuse_quantize(plan->g, plan->c, x_nchw, x_slot, in_scale)) {
     // the stem kernel's producer warps quantise the fp32 image straight into its operand ring
@@ -284,15 +304,17 @@ int i8ie_conv2d_f32_u8_indirect(i8ie_conv_plan* plan, const float* const* x_slot
   return conv2d_f32_u8(plan, nullptr, x_slot, in_scale, in_zp, y, oc, sb, sc, zp_out, flags, acc_out, stream);
 }
 
-int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
-               int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb, float sc,
-               int zp_out, int flags, int32_t* acc_out, int impl, void* stream) {
+static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+                 int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
+                 const float* sb_vec, float sb_min, float sb_max, float sc,
+                 int zp_out, int flags, int32_t* acc_out, int impl, void* stream) {
   I8IE_REQUIRE(x && w && y && oc && bias_f, "fc_u8: null argument");
   I8IE_REQUIRE(m > 0 && n > 0 && k > 0 && ldx % 16 == 0 && ldw % 16 == 0 && ldy % 16 == 0 && ldx >= k &&
                    ldw >= ldx && ldy >= n && n_pad >= n,
                "fc_u8: bad shape/pitch (m=%d n=%d k=%d ldx=%d ldw=%d ldy=%d n_pad=%d)", m, n, k, ldx, ldw, ldy, n_pad);
   I8IE_REQUIRE(zp_out >= 0 && zp_out <= 255, "fc_u8: zero point out of range");
   EpiParams ep{oc, bias_f, sa, sb, sc, zp_out, (flags & I8IE_EPI_RELU) ? 1 : 0, acc_out};
+  if (sb_vec != nullptr) { ep.sb_vec = sb_vec; ep.sb_min = sb_min; ep.sb_max = sb_max; }
   tc_error_sink_touch((cudaStream_t)stream);
   // shape dispatch: the tensor-core kernel needs at least one full 32-byte K step to be worthwhile
   const bool eligible = !tc_disabled() && k >= 32;
@@ -317,6 +339,22 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
   g.kh = 1; g.kw = 1; g.stride = 1; g.pad = 0;
   g.oh = 1; g.ow = 1; g.M = m; g.N = n; g.n_pad = n_pad; g.ldw = ldw; g.out_cp = ldy;
   return launch_simt_igemm(g, x, w, y, ep, 0, (cudaStream_t)stream);
+}
+
+int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+               int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb, float sc,
+               int zp_out, int flags, int32_t* acc_out, int impl, void* stream) {
+  return fc_u8(x, ldx, w, ldw, n_pad, y, ldy, m, n, k, oc, bias_f, sa, sb, nullptr, 0.f, 0.f, sc, zp_out, flags, acc_out,
+               impl, stream);
+}
+
+int i8ie_fc_u8_pc(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+                  int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, const float* sb_vec,
+                  float sb_min, float sb_max, float sc, int zp_out, int flags, int32_t* acc_out, int impl,
+                  void* stream) {
+  I8IE_REQUIRE(sb_vec != nullptr && sb_min > 0.f && sb_max >= sb_min, "fc_u8_pc: bad per-channel scales");
+  return fc_u8(x, ldx, w, ldw, n_pad, y, ldy, m, n, k, oc, bias_f, sa, sb_min, sb_vec, sb_min, sb_max, sc, zp_out, flags,
+               acc_out, impl, stream);
 }
 
 // Debug hook: first protocol error (timeout) recorded by a tensor-core kernel, 0 if none.

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(NT) simt_igemm_kernel(const GemmGeom g, const 
     const bool real = n < g.N;
     const int32_t ocn = real ? __ldg(ep.oc + n) : 0;
     const float bf = (real && ep.bias_f) ? __ldg(ep.bias_f + n) : 0.f;
+    const float sbn = (real && ep.sb_vec) ? __ldg(ep.sb_vec + n) : ep.sb;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = m0 + ty + 16 * i;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(NT) simt_igemm_kernel(const GemmGeom g, const 
         int32_t v = acc[i][j] + ocn;
         if (ep.bias_f) v = fc_bias_add(v, bf);
         if (ep.acc_out) ep.acc_out[(size_t)m * g.N + n] = v;
-        q = requant_u8(v, ep.sa, ep.sb, ep.sc, zpf);
+        q = requant_u8(v, ep.sa, sbn, ep.sc, zpf);
         if (ep.relu) q = max(q, (uint32_t)ep.zp_out);
       }
       y[(size_t)m * g.out_cp + n] = (uint8_t)q;
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) fc_head_kernel(const uint8_t*
     if (ep.bias_f) v = fc_bias_add(v, __ldg(ep.bias_f + lane));
     if (ep.acc_out) ep.acc_out[(size_t)m * n + lane] = v;
     const float zpf = (float)ep.zp_out;
-    q = fast ? requant_u8_fast(v, ep.sa, ep.sb, ep.sc, __frcp_rn(ep.sc), zpf) : requant_u8(v, ep.sa, ep.sb, ep.sc, zpf);
+    const float sbn = ep.sb_vec ? __ldg(ep.sb_vec + lane) : ep.sb;
+    q = fast ? requant_u8_fast(v, ep.sa, sbn, ep.sc, __frcp_rn(ep.sc), zpf) : requant_u8(v, ep.sa, sbn, ep.sc, zpf);
     if (ep.relu) q = max(q, (uint32_t)ep.zp_out);
   }
   y[(size_t)m * ldy + lane] = (uint8_t)q;
@@ -208,7 +210,7 @@ int launch_fc_head(const uint8_t* x, int ldx, const int8_t* w, int ldw, uint8_t*
                    const EpiParams& ep, cudaStream_t stream) {
   const int kvec = (k + 15) / 16;   // the [k, ldx) tail multiplies zero weight lanes
   launch_pdl(fc_head_kernel, dim3(m), dim3(kHeadWarps * 32), 0, stream, x, ldx, w, ldw, y, ldy, n, kvec, ep,
-             requant_fast_ok(ep.sa, ep.sb, ep.sc) ? 1 : 0);
+             requant_fast_ok(ep) ? 1 : 0);
   return check_launch("fc_head_kernel");
 }
 

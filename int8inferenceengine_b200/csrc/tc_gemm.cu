@@ -70,6 +70,7 @@ struct TcParams {
   // waits for its siblings, then folds + requantises ITS share of the tile's rows — no second kernel.
   int fused_reduce;
   unsigned* sk_counters;      // [tiles_m * tiles_n][2] = {arrived, finished}, zero between launches
+  int pf_weights;             // fc: L2-prefetch the weight blocks of a tile before streaming them
   // 128-row sub-tiles per CTA tile (1 or 2): two accumulators share every weight stage, which
   // cuts the L2->SM bytes per MAC (the binding limit of a 128 x BN tile, ~43 B/clk/SM)
   int mt;
@@ -117,6 +118,7 @@ struct alignas(16) TcControl {
   uint32_t pad_[3];
   int32_t oc[2][BN];
   float bias[2][BN];
+  float sbv[2][BN];   // per-output-channel weight scales of the tile (F4 extension; unused otherwise)
 };
 
 template <int BN, int BK>
@@ -132,7 +134,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 template <int BN, int NSUB = kEpiWarps / 4>   // NSUB warps share a quadrant and take every NSUB-th chunk
 __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, long long m, int n0,
                                              uint32_t s_oc, uint32_t s_bias, const int32_t* corr, float rcp,
-                                             int half) {
+                                             int half, uint32_t s_sb = 0) {
   const float zpf = (float)p.ep.zp_out;
   const float sa = p.ep.sa, sb = p.ep.sb, sc = p.ep.sc;
   const bool has_bias = p.ep.bias_f != nullptr;
@@ -183,12 +185,34 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (uint32_t)max((int32_t)v[j], 0);
       }
+      if (s_sb == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) requant2_u8_fast<false>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
+        for (int j = 0; j < 32; j += 2) requant2_u8_fast<false>((int32_t)v[j], (int32_t)v[j + 1], rq, v[j], v[j + 1]);
+      } else {   // per-output-channel weight scales (staged next to oc)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 s4 = ptx::lds128(s_sb + (uint32_t)(c0 + 4 * g) * 4);
+          requant2_u8_fast_sb<false>((int32_t)v[4 * g], (int32_t)v[4 * g + 1], rq,
+                                     f2_pack(__uint_as_float(s4.x), __uint_as_float(s4.y)), v[4 * g], v[4 * g + 1]);
+          requant2_u8_fast_sb<false>((int32_t)v[4 * g + 2], (int32_t)v[4 * g + 3], rq,
+                                     f2_pack(__uint_as_float(s4.z), __uint_as_float(s4.w)), v[4 * g + 2], v[4 * g + 3]);
+        }
+      }
     } else {
       const uint32_t zlo = p.ep.relu ? (uint32_t)p.ep.zp_out : 0u;
+      if (s_sb == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = max(requant_u8((int32_t)v[j], sa, sb, sc, zpf), zlo);
+        for (int j = 0; j < 32; ++j) v[j] = max(requant_u8((int32_t)v[j], sa, sb, sc, zpf), zlo);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 s4 = ptx::lds128(s_sb + (uint32_t)(c0 + 4 * g) * 4);
+          v[4 * g] = max(requant_u8((int32_t)v[4 * g], sa, __uint_as_float(s4.x), sc, zpf), zlo);
+          v[4 * g + 1] = max(requant_u8((int32_t)v[4 * g + 1], sa, __uint_as_float(s4.y), sc, zpf), zlo);
+          v[4 * g + 2] = max(requant_u8((int32_t)v[4 * g + 2], sa, __uint_as_float(s4.z), sc, zpf), zlo);
+          v[4 * g + 3] = max(requant_u8((int32_t)v[4 * g + 3], sa, __uint_as_float(s4.w), sc, zpf), zlo);
+        }
+      }
     }
     if (n0 + c0 + 32 > p.N) {   // pad lanes carry the zero point (warp-uniform branch)
 #pragma unroll
@@ -245,17 +269,16 @@ __device__ __forceinline__ void splitk_fused_finish(const TcParams& p, int split
     const int m = m0 + r;
     const int32_t* src = p.ws + (size_t)m * p.ws_ld + n4;
     int4 a = make_int4(0, 0, 0, 0);
-    int s = 0;
-    for (; s + 4 <= p.splits; s += 4) {
-      int4 v[4];
+    // up to 12 independent 128-bit L2 loads in flight per thread (the partials are L2-resident: the fold is
+    // latency-bound, not bandwidth-bound)
+    for (int s0 = 0; s0 < p.splits; s0 += 12) {
+      int4 v[12];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const int4*>(src + (size_t)(s + j) * split_stride));
+      for (int j = 0; j < 12; ++j)
+        v[j] = (s0 + j < p.splits) ? __ldcg(reinterpret_cast<const int4*>(src + (size_t)(s0 + j) * split_stride))
+                                   : make_int4(0, 0, 0, 0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
-    }
-    for (; s < p.splits; ++s) {
-      const int4 v = __ldcg(reinterpret_cast<const int4*>(src + (size_t)s * split_stride));
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      for (int j = 0; j < 12; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
     }
     const int32_t acc[4] = {a.x, a.y, a.z, a.w};
     uint32_t word = 0;
@@ -267,8 +290,9 @@ __device__ __forceinline__ void splitk_fused_finish(const TcParams& p, int split
         int32_t v = acc[j] + __ldg(p.ep.oc + n);
         if (p.ep.bias_f) v = fc_bias_add(v, __ldg(p.ep.bias_f + n));
         if (p.ep.acc_out) p.ep.acc_out[(size_t)m * p.N + n] = v;
-        const uint32_t y = p.fast_requant ? requant_u8_fast(v, p.ep.sa, p.ep.sb, p.ep.sc, rcp, zpf)
-                                          : requant_u8(v, p.ep.sa, p.ep.sb, p.ep.sc, zpf);
+        const float sbn = p.ep.sb_vec ? __ldg(p.ep.sb_vec + n) : p.ep.sb;
+        const uint32_t y = p.fast_requant ? requant_u8_fast(v, p.ep.sa, sbn, p.ep.sc, rcp, zpf)
+                                          : requant_u8(v, p.ep.sa, sbn, p.ep.sc, zpf);
         q = max(y, zlo);
       }
       word |= q << (8 * j);
@@ -334,6 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
         const int split = tile / mn_tiles, mn = tile % mn_tiles;
         const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
         const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+        if (MODE == 0 && p.pf_weights) {
+          // small-M fc = a weight stream from DRAM: ask for ALL weight blocks of this tile at once (L2 prefetch,
+          // see ptx::prefetch_l2_bulk); the ring's loads below then find them in L2 or on their way
+          for (int kb = kb0; kb < kb1; ++kb)
+            for (int j = 0; j < p.ksub; ++j) ptx::prefetch_l2_tensor_2d(&tmB, (kb * p.ksub + j) * BK, n0);
+        }
         int bw[MT] = {}, bh[MT] = {}, bn[MT] = {};
         if (MODE == 1) {
 #pragma unroll
@@ -436,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
           const int n = n0 + j;
           ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
           ctl->bias[ob][j] = (n < p.N && has_bias) ? __ldg(p.ep.bias_f + n) : 0.f;
+          if (p.ep.sb_vec) ctl->sbv[ob][j] = (n < p.N) ? __ldg(p.ep.sb_vec + n) : 1.f;
         }
         epi_bar_sync();
       }
@@ -478,7 +509,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
           if (!ok) tc_fail(3);
           ptx::tc_fence_after();
           epilogue_row<BN>(p, t_row, (m < p.M && ok) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
-                           ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
+                           ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2,
+                           p.ep.sb_vec ? ptx::smem_u32(ctl->sbv[ob]) : 0u);
         }
         // hand the accumulator buffer back to the MMA warp
         ptx::tc_fence_before();
@@ -624,6 +656,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
         const int n = n0 + j;
         ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
         ctl->bias[ob][j] = 0.f;
+        if (p.ep.sb_vec) ctl->sbv[ob][j] = (n < p.N) ? __ldg(p.ep.sb_vec + n) : 1.f;
       }
       epi_bar_sync();
       const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
@@ -643,7 +676,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
       if (!ok) tc_fail(3);
       ptx::tc_fence_after();
       epilogue_row<BN>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
-                       ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2);
+                       ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2,
+                       p.ep.sb_vec ? ptx::smem_u32(ctl->sbv[ob]) : 0u);
       // hand the accumulator buffer (both halves) back to the even CTA's MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -804,7 +838,15 @@ struct Stem2Params {
   float in_scale, fast_lim;
   int in_zp;
   int f_stages, f_stage_bytes;   // fp32 row ring: [rows_per_tile][c][w] floats per stage
+  int pf_tiles;                  // L2 prefetch distance of the fp32 rows, in tiles (0 = off)
+  // dev-only timeline (I8IE_STEM2_TRACE=<file>): CTA 0 records clock64() at kTraceEvents points of each of
+  // its first kTraceTiles tiles — trace[tile][event]; nullptr in production
+  long long* trace;
 };
+constexpr int kTraceTiles = 24, kTraceEvents = 16;
+__device__ __forceinline__ void stem_trace(const Stem2Params& sp, uint32_t it, int ev) {
+  if (sp.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceTiles) sp.trace[it * kTraceEvents + ev] = clock64();
+}
 
 // FQ: the input quantise is fused. Warp 0 bulk-copies the raw fp32 image rows of a tile
 // (cp.async.bulk, one row of one channel plane per copy) into a second shared-memory ring, 8
@@ -881,11 +923,27 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       // warps emit zero-point rows for them)
       const float* xf = sp.xslot ? *sp.xslot : sp.xf;
       const uint32_t frow_bytes = (uint32_t)sp.w * 4;
+      // The image comes from DRAM: lane ch prefetches channel plane ch of the rows of a LATER tile into L2
+      // (see ptx::prefetch_l2_bulk), so that the ring's bulk copies hit L2 when their turn comes.
+      const int pf_ahead = sp.pf_tiles;
+      auto prefetch_tile = [&](int t) {
+        if (t >= t_end || lane >= sp.c) return;
+        const int pimg = t / sp.pairs, pp0 = (t % sp.pairs) * 2;
+        const int pr0 = 4 * pp0 - sp.pad;
+        int plo = pr0 < 0 ? -pr0 : 0, phi = sp.h - pr0;
+        if (phi > rows_per_tile) phi = rows_per_tile;
+        if (!(t == t_begin || pp0 == 0) && plo < i_new) plo = i_new;
+        if (phi > plo)
+          ptx::prefetch_l2_bulk(xf + (((int64_t)pimg * sp.c + lane) * sp.h + (pr0 + plo)) * sp.w, (uint32_t)(phi - plo) * frow_bytes);
+      };
+      for (int t = t_begin; t < t_begin + pf_ahead; ++t) prefetch_tile(t);
       for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
         const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
         const uint32_t s = it % (uint32_t)sp.f_stages;
         const uint32_t ph = (it / (uint32_t)sp.f_stages) & 1;
+        if (pf_ahead > 0) prefetch_tile(tile + pf_ahead);
         if (!ptx::mbar_wait(&f_empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
+        if (lane == 0) stem_trace(sp, it, 0);
         const int r0 = 4 * p0 - sp.pad;                 // image row of tile row 0
         int lo = r0 < 0 ? -r0 : 0, hi = sp.h - r0;      // tile rows [lo, hi) lie inside the image
         if (hi > rows_per_tile) hi = rows_per_tile;
@@ -942,7 +1000,9 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const uint32_t s = it % (uint32_t)sp.stages;
       const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
       if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { tc_fail(4); alive = false; break; }
+      if (lane == 0) stem_trace(sp, it, 8);
       if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
+      if (lane == 0) stem_trace(sp, it, 9);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tbase + buf * acc_stride<BN>();
       const uint32_t a_lo0 = (((sa_base + s * (uint32_t)a_stage) & 0x3FFFFu) >> 4) | a_flags;
@@ -971,6 +1031,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         ptx::tc_commit(&ctl->empty[s]);
         ptx::tc_commit(&ctl->tmem_full[buf]);
       }
+      if (lane == 0) stem_trace(sp, it, 10);
       __syncwarp();
     }
     if (!alive && lane == 0) {
@@ -1012,10 +1073,13 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const bool first = tile == t_begin || p0 == 0;
       // (a timed-out warp keeps walking the loop without waiting, so that nobody hangs in bar.sync)
       if (!dead && !ptx::mbar_wait(&f_full[fs], fph)) { tc_fail(6); dead = true; }
+      if (pw == 0 && lane == 0) stem_trace(sp, it, 1);
       if (!dead && !ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); dead = true; }
+      if (pw == 0 && lane == 0) stem_trace(sp, it, 2);
       // every converter warp is done with the previous tile: its rows can be read, and the stage
       // before it (this tile's target) is no longer being read by a slower warp's copy
       asm volatile("bar.sync 2, %0;" ::"n"(32 * kProdW) : "memory");
+      if (pw == 0 && lane == 0) stem_trace(sp, it, 3);
       const uint32_t st = sA_u + s * (uint32_t)a_stage;
       const uint32_t sf = sF_u + fs * (uint32_t)sp.f_stage_bytes;
       int i_start = 0;
@@ -1031,6 +1095,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         }
         i_start = i_new;
       }
+      if (pw == 0 && lane == 0) stem_trace(sp, it, 4);
       for (int i = i_start + pw; i < nrows && !(sp.dbg & 16); i += kProdW) {
         const int row = i0 + i - sp.pad;
         const bool row_ok = row >= 0 && row < sp.h;
@@ -1086,6 +1151,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
           if (sx_ok[u]) ptx::sts128(drow + (uint32_t)(lane + 32 * u) * 16u, make_uint4(wd[0], wd[1], wd[2], wd[3]));
         }
       }
+      if (pw == 0 && lane == 0) stem_trace(sp, it, 5);
       // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -1093,6 +1159,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         ptx::mbar_arrive(&ctl->full[s]);
         ptx::mbar_arrive(&f_empty[fs]);
       }
+      if (pw == 0 && lane == 0) stem_trace(sp, it, 6);
     }
   } else {
     const int quad = warp & 3;
@@ -1102,6 +1169,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     for (int j = et; j < BN; j += 32 * kEpiW) {
       ctl->oc[0][j] = (j < p.N) ? __ldg(p.ep.oc + j) : 0;
       ctl->bias[0][j] = 0.f;
+      if (p.ep.sb_vec) ctl->sbv[0][j] = (j < p.N) ? __ldg(p.ep.sb_vec + j) : 1.f;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiW) : "memory");
     uint32_t it = 0;
@@ -1114,11 +1182,13 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const long long m = valid ? ((long long)img * sp.oh + prow) * sp.ow + q : -1ll;
       const bool ok = ptx::mbar_wait(&ctl->tmem_full[buf], bph);
       if (!ok) tc_fail(3);
+      if (warp == 2 && lane == 0) stem_trace(sp, it, 12);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + buf * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
       if (!(sp.dbg & 1)) {
         epilogue_row<BN, kEpiW / 4>(p, t_row, (ok && !(sp.dbg & 8)) ? m : -1ll, 0, ptx::smem_u32(ctl->oc[0]),
-                                    ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2);
+                                    ptx::smem_u32(ctl->bias[0]), nullptr, rcp, (warp - 2) >> 2,
+                                    p.ep.sb_vec ? ptx::smem_u32(ctl->sbv[0]) : 0u);
         // output pitch wider than the N tile (e.g. 96 channels stored at pitch 128): the pad lanes
         // carry the zero point; written by the warp of each pair that had fewer chunks
         if (BN < p.out_cp && ((warp - 2) >> 2) == ((BN / 32) % (kEpiW / 4)) && ok && m >= 0) {
@@ -1127,9 +1197,11 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
             *reinterpret_cast<uint4*>(p.y + (size_t)m * p.out_cp + c) = make_uint4(z4, z4, z4, z4);
         }
       }
+      if (warp == 2 && lane == 0) stem_trace(sp, it, 13);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+      if (warp == 2 && lane == 0) stem_trace(sp, it, 14);
     }
   }
   ptx::tc_fence_before();
@@ -1271,7 +1343,8 @@ __global__ void __launch_bounds__(256) fc_splitk_reduce_kernel(const int32_t* __
       int32_t v = acc[j] + __ldg(ep.oc + n);
       if (ep.bias_f) v = fc_bias_add(v, __ldg(ep.bias_f + n));
       if (ep.acc_out) ep.acc_out[(size_t)m * N + n] = v;
-      const uint32_t r = fast ? requant_u8_fast(v, ep.sa, ep.sb, ep.sc, rcp, zpf) : requant_u8(v, ep.sa, ep.sb, ep.sc, zpf);
+      const float sbn = ep.sb_vec ? __ldg(ep.sb_vec + n) : ep.sb;
+      const uint32_t r = fast ? requant_u8_fast(v, ep.sa, sbn, ep.sc, rcp, zpf) : requant_u8(v, ep.sa, sbn, ep.sc, zpf);
       q = max(r, zlo);
     }
     word |= q << (8 * j);
@@ -1650,7 +1723,7 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.num_kb = g.kh * g.kw * p.cblocks / p.ksub;
   p.kh = g.kh; p.kw = g.kw; p.stride_h = p.stride_w = g.stride; p.pad = g.pad; p.H = g.h; p.W = g.w; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = zp_in; p.border_tab = border_tab; p.y = y; p.ep = ep;
-  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  p.fast_requant = requant_fast_ok(ep);
   if (cluster == 2) {   // CTA pairs
     I8IE_REQUIRE(bk == 128, "tcgen05 pair: needs 128-byte K blocks");
     switch (bn) {
@@ -1702,7 +1775,10 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   p.cblocks = 1; p.ksub = 1; p.num_kb = (k + 127) / 128;
   p.kh = p.kw = 1; p.stride_h = p.stride_w = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
-  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  p.fast_requant = requant_fast_ok(ep);
+  // weights are read once per launch: a stream from DRAM whenever the batch is small
+  static const bool pf_ok = [] { const char* e = std::getenv("I8IE_FC_PREFETCH"); return !(e && e[0] == '0'); }();
+  p.pf_weights = (pf_ok && m <= 1024) ? 1 : 0;
   if (splits <= 1) return launch_bk<0>(128, bn, tmA, tmB, p, stream);
   // split K across CTAs, then fold the partial sums (exact: integer adds commute)
   p.splits = splits; p.kb_per = kb_per;
@@ -1712,7 +1788,7 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   int rc = ensure_workspace(part_bytes + kSkCounterBytes, stream, &p.ws);
   if (rc != I8IE_OK) return rc;
   // one kernel when every (split, tile) gets its own co-resident CTA; I8IE_FC_FUSED=0 keeps the two-kernel path
-  static const bool fused_ok = [] { const char* e = std::getenv("I8IE_FC_FUSED"); return !(e && e[0] == '0'); }();
+  static const bool fused_ok = [] { const char* e = std::getenv("I8IE_FC_FUSED"); return e && e[0] == '1'; }();
   if (fused_ok && mn_tiles * p.splits <= num_sms() && 2 * mn_tiles * (int)sizeof(unsigned) <= kSkCounterBytes) {
     p.fused_reduce = 1;
     p.sk_counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(g_ws) + g_ws_bytes - kSkCounterBytes);
@@ -1798,7 +1874,7 @@ int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.kh = g.kh; p.kw = 1; p.stride_h = g.stride; p.stride_w = g.stride / 4; p.pad = 0;
   p.H = (g.oh - 1) * g.stride + g.kh; p.W = (g.ow - 1) * (g.stride / 4) + 1; p.oh = g.oh; p.ow = g.ow;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
-  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  p.fast_requant = requant_fast_ok(ep);
   return launch_bk<1>(64, bn, tmA, tmB, p, stream);
 }
 
@@ -1824,6 +1900,16 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   }
   sp.dbg = 0;
   if (const char* e = std::getenv("I8IE_STEM2_DBG")) sp.dbg = std::atoi(e);
+  sp.pf_tiles = 8;
+  if (const char* e = std::getenv("I8IE_STEM2_PF")) sp.pf_tiles = std::atoi(e);
+  sp.trace = nullptr;
+  const char* trace_path = fq ? std::getenv("I8IE_STEM2_TRACE") : nullptr;
+  static long long* d_trace = nullptr;
+  if (trace_path != nullptr) {   // dev only: eager launches, synchronises
+    if (d_trace == nullptr) I8IE_CUDA_OK(cudaMalloc(&d_trace, sizeof(long long) * kTraceTiles * kTraceEvents));
+    I8IE_CUDA_OK(cudaMemset(d_trace, 0, sizeof(long long) * kTraceTiles * kTraceEvents));
+    sp.trace = d_trace;
+  }
 
   const int w_bytes = g.kh * BN * 64;
   const int a_stage = 4 * sp.nsl * 1024;
@@ -1859,6 +1945,23 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const int threads = fq ? stem_threads<BN, true>() : stem_threads<BN, false>();
   launch_pdl(kern, dim3(grid), dim3(threads), (size_t)smem, stream, tmB, p, sp);
+  if (trace_path != nullptr) {
+    std::vector<long long> h(kTraceTiles * kTraceEvents);
+    I8IE_CUDA_OK(cudaDeviceSynchronize());
+    I8IE_CUDA_OK(cudaMemcpy(h.data(), d_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    if (FILE* f = std::fopen(trace_path, "w")) {
+      long long t0 = 0;
+      for (long long v : h) if (v != 0 && (t0 == 0 || v < t0)) t0 = v;
+      std::fprintf(f, "# tile: ev0 prod f_empty | 1 conv f_full 2 conv empty 3 conv bar 4 conv copied 5 conv converted 6 conv arrived | "
+                      "8 mma tmem_empty 9 mma full 10 mma committed | 12 epi tmem_full 13 epi done 14 epi arrived (clocks since first event)\n");
+      for (int t = 0; t < kTraceTiles; ++t) {
+        std::fprintf(f, "%2d:", t);
+        for (int e = 0; e < kTraceEvents; ++e) std::fprintf(f, " %7lld", h[t * kTraceEvents + e] ? h[t * kTraceEvents + e] - t0 : -1ll);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+    }
+  }
   return check_launch("tc_stem2_kernel");
 }
 
@@ -1877,7 +1980,7 @@ int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
-  p.fast_requant = requant_fast_ok(ep.sa, ep.sb, ep.sc);
+  p.fast_requant = requant_fast_ok(ep);
   I8IE_REQUIRE(bn % 32 == 0 || bn >= g.out_cp, "stem2: N tile %d narrower than the output pitch must be a multiple of 32", bn);
   switch (bn) {
     case 32:  return launch_stem2_bn<32>(g, s, xs, f32, tmB, p, stream);

@@ -52,11 +52,15 @@ class TopologyModule(api.Module):
             self.__dict__[name].layer.set_qparams(s, z)
 
 
-def build_module(topology, state_dict, qparams=None, calib=None):
+def build_module(topology, state_dict, qparams=None, calib=None, per_channel=False):
     """Module with weights loaded and converted. Either inject `qparams`
-    ({layer: (scale, zp)}) or pass a calibration batch `calib` (numpy NCHW f32)."""
+    ({layer: (scale, zp)}) or pass a calibration batch `calib` (numpy NCHW f32).
+    per_channel=True (extension, not in the reference): per-output-channel weight scales."""
     m = TopologyModule(topology)
     m.load(state_dict)
+    if per_channel:
+        for L in m.layers().values():
+            L.layer.per_channel = True
     if qparams is not None:
         m.set_qparams(qparams)
     elif calib is not None:

@@ -106,6 +106,45 @@ def quantize_weight(w, b):
     return qw, qb, np.float32(s)
 
 
+# ---- F4 extension (NOT in the reference): per-output-channel weight scales -------------------------
+# Pure compositions of the pinned functions above: layer.cc:6-26 applied to each output channel's
+# weights + its bias entry on its own, and quantize_utils.cc:27-36 applied per channel with that
+# channel's weight scale. The integer GEMM, the oc offsets and the fc float-bias add do not involve
+# the weight scale, so the accumulators come from the unchanged restatement.
+def quantize_weight_per_channel(w, b):
+    """-> (qw s8, qb s8, scales f32[n])"""
+    w = _c(w, np.float32)
+    b = _c(b, np.float32)
+    qw = np.empty(w.shape, np.int8)
+    qb = np.empty(b.shape, np.int8)
+    sc = np.empty(w.shape[0], np.float32)
+    for j in range(w.shape[0]):
+        qwj, qbj, sj = quantize_weight(w[j].reshape(-1), b[j:j + 1])
+        qw[j] = qwj.reshape(w[j].shape)
+        qb[j] = qbj[0]
+        sc[j] = sj
+    return qw, qb, sc
+
+
+def conv2d_u8_pc(x, qw, qb, stride, pad, in_scale, in_zp, w_scales, out_scale, out_zp, want_acc=False):
+    _, acc = conv2d_u8(x, qw, qb, stride, pad, in_scale, in_zp, np.float32(1.0), out_scale, out_zp, want_acc=True)
+    n, _, kc = acc.shape
+    oh = (x.shape[2] - qw.shape[2] + 2 * pad) // stride + 1
+    ow = (x.shape[3] - qw.shape[3] + 2 * pad) // stride + 1
+    out = np.empty((n, kc, oh, ow), np.uint8)
+    for j in range(kc):
+        out[:, j] = down_scale(np.ascontiguousarray(acc[:, :, j]), in_scale, w_scales[j], out_scale, out_zp).reshape(n, oh, ow)
+    return (out, acc) if want_acc else out
+
+
+def linear_u8_pc(x, qw, qb, in_scale, in_zp, w_scales, out_scale, out_zp, want_acc=False):
+    _, acc = linear_u8(x, qw, qb, in_scale, in_zp, np.float32(1.0), out_scale, out_zp, want_acc=True)
+    out = np.empty(acc.shape, np.uint8)
+    for j in range(acc.shape[1]):
+        out[:, j] = down_scale(np.ascontiguousarray(acc[:, j]), in_scale, w_scales[j], out_scale, out_zp)
+    return (out, acc) if want_acc else out
+
+
 def conv_offsets(qw, qb, in_zp, in_scale):
     qw = _c(qw, np.int8)
     kc = qw.shape[0]

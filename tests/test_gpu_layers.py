@@ -128,3 +128,106 @@ def test_fc_bias_float_roundtrip_above_2_24():
     out = L._forward_u8(u8_tensor_from_nchw(q, 0.025, 3), acc_out=acc)
     assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc)
     assert np.array_equal(out.numpy(), exp)
+
+
+# ---- F4 extension: per-output-channel weight scales (opt-in; the default stays the reference's) ----------
+PC_CONV = [  # n, c, h, w, kc, k, stride, pad -> one geometry per kernel family
+    (2, 3, 20, 20, 20, 5, 1, 0),          # SIMT dp4a (cp = 16)
+    (2, 32, 8, 8, 40, 3, 1, 1),           # single-CTA tcgen05 (BK 32)
+    (3, 256, 13, 13, 384, 3, 1, 1),       # CTA-pair tcgen05
+    (3, 96, 27, 27, 256, 5, 1, 2),        # row mode
+    (2, 3, 67, 67, 32, 11, 4, 2),         # stem
+]
+
+
+@pytest.mark.parametrize("geom", PC_CONV)
+def test_conv_per_channel_scales(geom):
+    import torch
+    from int8inferenceengine_b200 import backend as B
+    n, c, h, w_, kc, k, s, p = geom
+    rng = np.random.default_rng(sum(geom) + 3)
+    a = np.sqrt(6.0 / (c * k * k))
+    # channels of very different magnitude: where per-channel scales matter
+    w = (rng.uniform(-a, a, size=(kc, c, k, k)) * rng.uniform(0.05, 1.0, size=(kc, 1, 1, 1))).astype(np.float32)
+    b = rng.uniform(-0.02, 0.02, size=(kc,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(n, c, h, w_), dtype=np.uint8)
+    in_scale, in_zp, out_scale, out_zp = np.float32(0.025), 127, np.float32(0.03), 100
+    L = B.Conv2d(c, kc, k, s, p)
+    L.load_weight(w)
+    L.load_bias(b)
+    L.set_qparams(out_scale, out_zp)
+    L.per_channel = True
+    L.convert()
+    qw, qb, ws = port.quantize_weight_per_channel(w, b)
+    assert np.array_equal(L.q_weight().numpy(), qw) and np.array_equal(L.q_bias().numpy(), qb)
+    assert np.array_equal(L.weight_scales(), ws)
+    exp, exp_acc = port.conv2d_u8_pc(q, qw, qb, s, p, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    oh, ow = exp.shape[2], exp.shape[3]
+    acc = torch.empty(n * oh * ow * kc, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc)
+    assert np.array_equal(acc.cpu().numpy().reshape(n, oh * ow, kc), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), relu=True)
+    assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
+    # the scales matter: the per-tensor result differs
+    assert not np.array_equal(exp, port.conv2d_u8(q, *port.quantize_weight(w, b)[:2], s, p, in_scale, in_zp,
+                                                   port.quantize_weight(w, b)[2], out_scale, out_zp))
+
+
+@pytest.mark.parametrize("shape", [(5, 4096, 10), (100, 9216, 512), (130, 300, 200), (3, 20, 7)])
+def test_linear_per_channel_scales(shape):
+    import torch
+    from int8inferenceengine_b200 import backend as B
+    m, k, n = shape
+    rng = np.random.default_rng(m + k + n)
+    a = np.sqrt(6.0 / k)
+    w = (rng.uniform(-a, a, size=(n, k)) * rng.uniform(0.05, 1.0, size=(n, 1))).astype(np.float32)
+    b = rng.uniform(-0.02, 0.02, size=(n,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(m, k), dtype=np.uint8)
+    in_scale, in_zp, out_scale, out_zp = np.float32(0.0518), 116, np.float32(0.09), 127
+    L = B.Linear(k, n)
+    L.load_weight(w)
+    L.load_bias(b)
+    L.set_qparams(out_scale, out_zp)
+    L.per_channel = True
+    L.convert()
+    qw, qb, ws = port.quantize_weight_per_channel(w, b)
+    exp, exp_acc = port.linear_u8_pc(q, qw, qb, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    acc = torch.empty(m * n, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc)
+    assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc)
+    assert np.array_equal(out.numpy(), exp)
+
+
+def test_per_channel_net_runs_and_default_is_untouched():
+    """A whole topology with per-channel scales agrees with the composed oracle; the same topology without
+    the option still equals the reference golden logits (covered by test_gpu_nets)."""
+    import i8ie
+    from int8inferenceengine_b200 import workloads as W
+    from int8inferenceengine_b200.runner import build_module
+    topo = "mini_alex"
+    sd = W.make_weights(topo, 0)
+    m0 = build_module(topo, sd, calib=W.make_images(topo, 100, 1))
+    qp = {nm: (np.float32(L.layer._scale), int(L.layer._zp)) for nm, L in m0.layers().items()}
+    m = build_module(topo, sd, qparams=qp, per_channel=True)
+    x = W.make_images(topo, 9, 2)
+    got = m(i8ie.tensor(x)).numpy()
+    # composed oracle forward
+    qx = port.quantize(x, W.INPUT_SCALE, W.INPUT_ZP)
+    scale, zp = np.float32(W.INPUT_SCALE), W.INPUT_ZP
+    for op in W.TOPOLOGIES[topo]["ops"]:
+        if op[0] == "conv":
+            qw, qb, ws = port.quantize_weight_per_channel(sd[op[1] + ".weight"], sd[op[1] + ".bias"])
+            qx = port.conv2d_u8_pc(qx, qw, qb, op[5], op[6], scale, zp, ws, *qp[op[1]])
+            scale, zp = qp[op[1]]
+        elif op[0] == "fc":
+            qw, qb, ws = port.quantize_weight_per_channel(sd[op[1] + ".weight"], sd[op[1] + ".bias"])
+            qx = port.linear_u8_pc(qx, qw, qb, scale, zp, ws, *qp[op[1]])
+            scale, zp = qp[op[1]]
+        elif op[0] == "relu":
+            qx = port.relu_u8(qx, zp)
+        elif op[0] == "pool":
+            qx = port.max_pool2d_u8(qx, op[1], op[2])
+        else:
+            qx = qx.reshape(-1, op[1])
+    assert np.array_equal(got, port.dequantize(qx, scale, zp))

@@ -101,3 +101,28 @@ def test_alexnet_golden():
     for (tag, arr, _, _), sha in zip(recs, g["op_sha256"]):
         assert hashlib.sha256(arr.tobytes()).hexdigest() == str(sha), tag
     assert np.array_equal(logits, g["logits"])
+
+
+def test_per_channel_extension_reduces_to_the_reference_when_scales_are_equal():
+    """The F4 oracle extension is a composition of the pinned functions: with every channel given the
+    per-tensor scale it must reproduce the reference results exactly."""
+    from oracle import port
+    rng = np.random.default_rng(11)
+    w = rng.uniform(-0.2, 0.2, size=(12, 5, 3, 3)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(12,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(2, 5, 9, 9), dtype=np.uint8)
+    qw, qb, ws = port.quantize_weight(w, b)
+    ref = port.conv2d_u8(q, qw, qb, 1, 1, np.float32(0.03), 90, ws, np.float32(0.05), 120)
+    got = port.conv2d_u8_pc(q, qw, qb, 1, 1, np.float32(0.03), 90, np.full(12, ws, np.float32), np.float32(0.05), 120)
+    assert np.array_equal(ref, got)
+    w2 = rng.uniform(-0.2, 0.2, size=(7, 40)).astype(np.float32)
+    b2 = rng.uniform(-0.05, 0.05, size=(7,)).astype(np.float32)
+    x2 = rng.integers(0, 256, size=(6, 40), dtype=np.uint8)
+    qw2, qb2, ws2 = port.quantize_weight(w2, b2)
+    assert np.array_equal(port.linear_u8(x2, qw2, qb2, np.float32(0.03), 90, ws2, np.float32(0.05), 120),
+                          port.linear_u8_pc(x2, qw2, qb2, np.float32(0.03), 90, np.full(7, ws2, np.float32), np.float32(0.05), 120))
+    # per-channel weight quantisation = layer.cc:6-26 applied to each channel on its own
+    qw3, qb3, s3 = port.quantize_weight_per_channel(w2, b2)
+    for j in range(7):
+        a, c, sj = port.quantize_weight(w2[j], b2[j:j + 1])
+        assert np.array_equal(a, qw3[j]) and c[0] == qb3[j] and sj == s3[j]

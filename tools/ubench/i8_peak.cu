@@ -136,6 +136,36 @@ __global__ void __launch_bounds__(128, 1) l2_stream_kernel(const uint8_t* __rest
   }
 }
 
+// ---- DRAM -> SM through bulk copies: same ring, chunk size and ring depth as parameters, every chunk a
+// DRAM miss (each CTA walks its own region of a buffer far larger than L2, touched once) ------------------
+__global__ void __launch_bounds__(128, 1) dram_stream_kernel(const uint8_t* __restrict__ src, size_t region_bytes,
+                                                             int chunk, int slots, int chunks, long long* cycles,
+                                                             int prefetch_ahead) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + 8 * 16384);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) ptx::mbar_init(&ctl->full[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint8_t* base = src + (size_t)blockIdx.x * region_bytes;
+    for (int c = 0; c < prefetch_ahead && c < chunks; ++c) ptx::prefetch_l2_bulk(base + (size_t)c * chunk, chunk);
+    const long long t0 = clock64();
+    for (int c = 0; c < chunks + slots; ++c) {
+      const int s = c % slots;
+      if (c >= slots && !ptx::mbar_wait(&ctl->full[s], ((c - slots) / slots) & 1)) { atomicExch(&g_err, 4); break; }
+      if (c < chunks) {
+        if (prefetch_ahead > 0 && c + prefetch_ahead < chunks) ptx::prefetch_l2_bulk(base + (size_t)(c + prefetch_ahead) * chunk, chunk);
+        ptx::mbar_arrive_expect_tx(&ctl->full[s], chunk);
+        ptx::bulk_load_1d(smem + s * 16384, base + (size_t)c * chunk, chunk, &ctl->full[s]);
+      }
+    }
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+
 // ---- both at once: warp 0 issues MMAs (single CTA, N = 256), warp 1 streams from L2 ----------------
 __global__ void __launch_bounds__(128, 1) both_kernel(int batches, int per, const uint8_t* __restrict__ src,
                                                       size_t slice_bytes, int chunks, long long* cycles) {
@@ -290,6 +320,41 @@ int main(int argc, char** argv) {
              ctas, shared, best, bytes / (best * 1e-3) / 1e9, (double)chunks * 16384 / clk, (double)chunks * 16384 / clk * ctas);
       fflush(stdout);
     }
+  }
+
+  // DRAM -> SM bulk-copy stream (every chunk misses L2): how much must be in flight per SM?
+  {
+    const size_t region = 8u << 20;   // 8 MB per CTA, 1.2 GB in all: nothing is re-read
+    uint8_t* big;
+    CK(cudaMalloc(&big, region * sms));
+    CK(cudaMemset(big, 1, region * sms));
+    CK(cudaFuncSetAttribute(dram_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l2));
+    uint8_t* flush;
+    CK(cudaMalloc(&flush, 256u << 20));
+    for (int chunk : {7168, 16384}) {
+      for (int slots : {3, 8}) {
+        for (int pf : {0, 16}) {
+          const int chunks = (int)(region / chunk);
+          CK(cudaMemset(flush, 2, 256u << 20));   // evict the region from L2
+          CK(cudaMemset(d_cyc, 0, sizeof(long long) * 1024));
+          CK(cudaEventRecord(e0));
+          dram_stream_kernel<<<sms, 128, smem_l2>>>(big, region, chunk, slots, chunks, d_cyc, pf);
+          CK(cudaEventRecord(e1));
+          CK(cudaEventSynchronize(e1));
+          float ms;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          std::vector<long long> cyc(sms);
+          CK(cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+          const double bytes = (double)chunks * chunk * sms;
+          printf("{\"bench\": \"dram_bulk\", \"chunk\": %d, \"in_flight\": %d, \"l2_prefetch_ahead\": %d, \"ms\": %.4f, "
+                 "\"gbs\": %.1f, \"bytes_per_clk_per_sm\": %.2f}\n",
+                 chunk, slots, pf, ms, bytes / (ms * 1e-3) / 1e9, (double)chunks * chunk / med(cyc));
+          fflush(stdout);
+        }
+      }
+    }
+    CK(cudaFree(flush));
+    CK(cudaFree(big));
   }
 
   // both at once
