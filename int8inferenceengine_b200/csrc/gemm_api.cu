@@ -57,6 +57,7 @@ struct i8ie_conv_plan {
   int c;     // real input channels
   // tcgen05 state
   int bk, bn;
+  int pair_mt;          // pair kernel: 256-row accumulators per tile (1 or 2)
   int cluster;          // CTAs per cluster (weight tile multicast); tmB's box holds bn / cluster rows
   CUtensorMap tmB;
   int32_t* border_tab;  // device, owned
@@ -124,6 +125,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   p->sb_min = p->sb_max = 0.f;
   p->c = c;
   p->cluster = 1;
+  p->pair_mt = 1;
   if (impl == 4) {
     // row mode: x will be the physically padded tensor [n][h + 2p][w + 2p][cp]
     if (tc_disabled() || !tc_row_mode_ok(c, kh, kw, stride, pad, out_cp) || cp != (c + 15) / 16 * 16) {
@@ -136,7 +138,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
     p->kr = tc_row_mode_kr(cp, kw);
     p->gv = tc_row_mode_geom(g, p->kr);
     p->bk = 128;
-    p->bn = tc_pick_bn_pair(p->gv, 128);
+    p->bn = tc_pick_bn_pair(p->gv, 128, &p->pair_mt);
     p->cluster = tc_conv_cluster(128, p->bn);
     int rc4 = I8IE_OK;
     if (p->cluster != 2) { set_error("conv2d_plan_create: row mode needs the pair kernel (bn=%d)", p->bn); rc4 = I8IE_EINVAL; }
@@ -194,7 +196,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   }
   if (rc == I8IE_OK && p->impl == 2) {
     p->bk = tc_conv_bk(g);
-    p->bn = tc_pick_bn_pair(g, p->bk);   // every lane of the padded output pitch is written
+    p->bn = tc_pick_bn_pair(g, p->bk, &p->pair_mt);   // every lane of the padded output pitch is written
     p->cluster = tc_conv_cluster(p->bk, p->bn);
     rc = tc_encode_weight_map(&p->tmB, w_packed, kc_pad, g.ldw, p->bk, p->cluster > 1 ? tc_pair_box_rows(p->bn) : p->bn);
     const int tab = tc_border_table_size(g);
@@ -255,7 +257,8 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
     int rc = plan->amaps.get(x, 4, 0, 0, 0, &tmA,
                              [&](CUtensorMap* m) { return tc_encode_act_map_row_mode(m, x, plan->g, plan->kr); });
     if (rc != I8IE_OK) return rc;
-    return launch_tc_conv(plan->gv, tmA, plan->tmB, 128, plan->bn, 2, nullptr, y, ep, zp_in, (cudaStream_t)stream);
+    return launch_tc_conv(plan->gv, tmA, plan->tmB, 128, plan->bn, 2, nullptr, y, ep, zp_in, (cudaStream_t)stream,
+                          plan->pair_mt);
   }
   if (plan->impl == 2) {
     CUtensorMap tmA;
@@ -263,7 +266,7 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
                              [&](CUtensorMap* m) { return tc_encode_act_map_im2col(m, x, plan->g, plan->bk); });
     if (rc != I8IE_OK) return rc;
     return launch_tc_conv(plan->g, tmA, plan->tmB, plan->bk, plan->bn, plan->cluster, plan->border_tab, y, ep, zp_in,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, plan->pair_mt);
   }
   return launch_simt_igemm(plan->g, x, plan->w_packed, y, ep, zp_in, (cudaStream_t)stream);
 }

@@ -45,9 +45,10 @@ int tc_encode_act_map_row_mode(CUtensorMap* tm, const uint8_t* x, const GemmGeom
 GemmGeom tc_row_mode_geom(const GemmGeom& g, int kr);
 int tc_conv_cluster(int bk, int bn);   // 2 = CTA-pair kernel (cta_group::2), 1 = single CTAs
 int tc_pair_box_rows(int bn);          // weight-map box rows of the pair kernel
-int tc_pick_bn_pair(const GemmGeom& g, int bk);   // cost-model N tile for conv plans (pair kernel candidates)
+int tc_pick_bn_pair(const GemmGeom& g, int bk, int* mt_out);   // cost-model tile for conv plans: N width, accumulators per tile
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
-                   const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream);
+                   const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream,
+                   int pair_mt = 1);
 void tc_fc_config(int m, int ldy, int k, int* bn, int* splits, int* kb_per);
 int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
                  int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream);

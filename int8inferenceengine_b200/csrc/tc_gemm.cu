@@ -65,12 +65,6 @@ struct TcParams {
   int splits, kb_per;
   int32_t* ws;                // [splits][M][ws_ld]
   int ws_ld;
-  // fused split-K finish: every CTA owns exactly ONE (split, tile) and all of them are co-resident
-  // (cooperative launch). After dumping its partial tile a CTA announces it on sk_counters[2*mn],
-  // waits for its siblings, then folds + requantises ITS share of the tile's rows — no second kernel.
-  int fused_reduce;
-  unsigned* sk_counters;      // [tiles_m * tiles_n][2] = {arrived, finished}, zero between launches
-  int pf_weights;             // fc: L2-prefetch the weight blocks of a tile before streaming them
   // 128-row sub-tiles per CTA tile (1 or 2): two accumulators share every weight stage, which
   // cuts the L2->SM bytes per MAC (the binding limit of a 128 x BN tile, ~43 B/clk/SM)
   int mt;
@@ -83,6 +77,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant (warp % 4), alternating 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
+// Pair kernel: four epilogue warps per TMEM lane quadrant. One 32 x 32 chunk costs a warp ~1000 clk (TMEM load,
+// ~250 dependent-ish instructions, two stores), and with the wide single-accumulator tiles (BN = 384, 512 x 256)
+// the epilogue of a tile is exposed: 16 warps halve it (and the tail of every launch).
+constexpr int kEpiWarps2 = 16;
+constexpr int kThreads2 = 64 + 32 * kEpiWarps2;
+__device__ __forceinline__ void epi_bar_sync2() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory"); }
 // stem kernel: its K is tiny (22 MMAs per tile), so the fp32 epilogue is the longest stage; with two
 // warps per sub-partition it runs latency-bound, four warps per sub-partition hide the dependent chains
 constexpr int kStemEpiWarps = 16;
@@ -232,83 +232,6 @@ __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, 
   }
 }
 
-// Fused split-K finish (small-M fc, see TcParams::fused_reduce), run by the 8 epilogue warps of a CTA
-// right after they dumped the CTA's partial tile: release the partials (fence + barrier + one atomic
-// add on the tile's counter), wait until all `splits` sibling CTAs have done the same, then fold and
-// requantise the rows split, split + splits, ... of the tile: y = requant(sum_s ws[s] + oc (+ bias)).
-// Integer adds commute, so the result does not depend on the order (bit-exact, fully_connected.cc:39-48).
-template <int BN>
-__device__ __forceinline__ void splitk_fused_finish(const TcParams& p, int split, int mn, int m0, int n0, int et,
-                                                    float rcp) {
-  __threadfence();   // this thread's partial stores are visible at GPU scope before the arrival below
-  epi_bar_sync();
-  unsigned* cnt = p.sk_counters + 2 * mn;
-  if (et == 0) {
-    atomicAdd(cnt, 1u);
-    long long t0 = 0;
-    for (unsigned n = 0;; ++n) {
-      unsigned v;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-      if (v >= (unsigned)p.splits) break;
-      if ((n & 63u) == 63u) {
-        const long long t = clock64();
-        if (t0 == 0) t0 = t;
-        else if (t - t0 > 4000000000ll) { tc_fail(8); break; }
-      }
-    }
-  }
-  epi_bar_sync();   // (the acquire above + this barrier order every epilogue thread's reads after the siblings' stores)
-  const int rows = min(BM, p.M - m0);
-  const int quads = min(BN, p.out_cp - n0) >> 2;          // 4-channel groups of this N tile
-  const size_t split_stride = (size_t)p.M * p.ws_ld;
-  const float zpf = (float)p.ep.zp_out;
-  const uint32_t zlo = p.ep.relu ? (uint32_t)p.ep.zp_out : 0u;
-  // thread -> (row slot, channel quad): consecutive threads read consecutive 16-byte groups of one row
-  for (int idx = et; idx < ((rows - split + p.splits - 1) / p.splits) * quads; idx += 32 * kEpiWarps) {
-    const int r = split + (idx / quads) * p.splits, n4 = n0 + (idx % quads) * 4;
-    const int m = m0 + r;
-    const int32_t* src = p.ws + (size_t)m * p.ws_ld + n4;
-    int4 a = make_int4(0, 0, 0, 0);
-    // up to 12 independent 128-bit L2 loads in flight per thread (the partials are L2-resident: the fold is
-    // latency-bound, not bandwidth-bound)
-    for (int s0 = 0; s0 < p.splits; s0 += 12) {
-      int4 v[12];
-#pragma unroll
-      for (int j = 0; j < 12; ++j)
-        v[j] = (s0 + j < p.splits) ? __ldcg(reinterpret_cast<const int4*>(src + (size_t)(s0 + j) * split_stride))
-                                   : make_int4(0, 0, 0, 0);
-#pragma unroll
-      for (int j = 0; j < 12; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
-    }
-    const int32_t acc[4] = {a.x, a.y, a.z, a.w};
-    uint32_t word = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n4 + j;
-      uint32_t q = (uint32_t)p.ep.zp_out;   // pad lanes carry the zero point
-      if (n < p.N) {
-        int32_t v = acc[j] + __ldg(p.ep.oc + n);
-        if (p.ep.bias_f) v = fc_bias_add(v, __ldg(p.ep.bias_f + n));
-        if (p.ep.acc_out) p.ep.acc_out[(size_t)m * p.N + n] = v;
-        const float sbn = p.ep.sb_vec ? __ldg(p.ep.sb_vec + n) : p.ep.sb;
-        const uint32_t y = p.fast_requant ? requant_u8_fast(v, p.ep.sa, sbn, p.ep.sc, rcp, zpf)
-                                          : requant_u8(v, p.ep.sa, sbn, p.ep.sc, zpf);
-        q = max(y, zlo);
-      }
-      word |= q << (8 * j);
-    }
-    *reinterpret_cast<uint32_t*>(p.y + (size_t)m * p.out_cp + n4) = word;
-  }
-  // the last CTA of the tile to finish re-arms the counters for the next launch
-  epi_bar_sync();
-  if (et == 0) {
-    if (atomicAdd(cnt + 1, 1u) == (unsigned)p.splits - 1u) {
-      cnt[0] = 0u; cnt[1] = 0u;
-      __threadfence();
-    }
-  }
-}
-
 // Persistent, warp-specialised implicit GEMM. MODE 0: A rows via a 2-D tiled map (fc);
 // MODE 1: A gathered by the TMA im2col engine (conv, incl. the stem view).
 template <int BN, int BK, int MODE, int MT>
@@ -350,83 +273,87 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
-    // ===== TMA producer: runs ahead across tile boundaries, the ring never drains =====
-    if (lane == 0) {
-      uint32_t it = 0;
-      bool alive = true;
-      for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
-        const int split = tile / mn_tiles, mn = tile % mn_tiles;
-        const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
-        const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
-        if (MODE == 0 && p.pf_weights) {
-          // small-M fc = a weight stream from DRAM: ask for ALL weight blocks of this tile at once (L2 prefetch,
-          // see ptx::prefetch_l2_bulk); the ring's loads below then find them in L2 or on their way
-          for (int kb = kb0; kb < kb1; ++kb)
-            for (int j = 0; j < p.ksub; ++j) ptx::prefetch_l2_tensor_2d(&tmB, (kb * p.ksub + j) * BK, n0);
-        }
-        int bw[MT] = {}, bh[MT] = {}, bn[MT] = {};
-        if (MODE == 1) {
+    // ===== TMA producer: runs ahead across tile boundaries, the ring never drains. The whole warp walks the
+    // loop (warp-uniform operands), one elected lane issues; ring cursors advance incrementally =====
+    const uint32_t smem_a = ptx::smem_u32(smem);
+    const uint32_t full_a = ptx::smem_u32(&ctl->full[0]), empty_a = ptx::smem_u32(&ctl->empty[0]);
+    const uint32_t nstages = (uint32_t)p.stages;
+    uint32_t s = 0, ph = 0;
+    bool alive = true;
+    for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
+      const int split = tile / mn_tiles, mn = tile % mn_tiles;
+      const int m0 = (mn / p.tiles_n) * BM * mt, n0 = (mn % p.tiles_n) * BN;
+      const int kb0 = split * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+      int bw[MT] = {}, bh[MT] = {}, bn[MT] = {};
+      if (MODE == 1) {
 #pragma unroll
-          for (int t = 0; t < mt; ++t) {
-            const int mm = m0 + t * BM;
-            const int q = mm % p.ow, r = mm / p.ow;
-            bw[t] = q * p.stride_w - p.pad;
-            bh[t] = (r % p.oh) * p.stride_h - p.pad;
-            bn[t] = r / p.oh;
-          }
+        for (int t = 0; t < mt; ++t) {
+          const int mm = m0 + t * BM;
+          const int q = mm % p.ow, r = mm / p.ow;
+          bw[t] = q * p.stride_w - p.pad;
+          bh[t] = (r % p.oh) * p.stride_h - p.pad;
+          bn[t] = r / p.oh;
         }
-        int cb = 0, kx = 0, ky = 0;   // (split-K is only used with MODE 0, where these stay 0)
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
-          ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)kStage);
-          uint8_t* sa = smem + (size_t)s * kStage;
-          uint8_t* sb = sa + p.ksub * mt * kSubA;
-          for (int j = 0; j < p.ksub; ++j) {
-            const int kidx = kb * p.ksub + j;   // BK-byte sub-block index along K
+      }
+      int cb = 0, kx = 0, ky = 0;   // (split-K is only used with MODE 0, where these stay 0)
+      int kcol = kb0 * p.ksub * BK;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!ptx::mbar_wait_a(empty_a + 8u * s, ph ^ 1u)) { tc_fail(1); alive = false; break; }
+        const bool el = ptx::elect_one_sync();
+        const uint32_t fb = full_a + 8u * s;
+        if (el) ptx::mbar_arrive_expect_tx_a(fb, (uint32_t)kStage);
+        const uint32_t sa = smem_a + s * (uint32_t)kStage;
+        const uint32_t sb = sa + (uint32_t)(p.ksub * mt * kSubA);
+        for (int j = 0; j < p.ksub; ++j) {
+          if (el) {
 #pragma unroll
             for (int t = 0; t < mt; ++t) {
-              uint8_t* dst = sa + (j * mt + t) * kSubA;
+              const uint32_t dst = sa + (uint32_t)((j * mt + t) * kSubA);
               if (MODE == 1)
-                ptx::tma_load_im2col_4d(dst, &tmA, &ctl->full[s], cb * BK, bw[t], bh[t], bn[t], (uint16_t)kx, (uint16_t)ky);
+                ptx::tma_load_im2col_4d_a(dst, &tmA, fb, cb, bw[t], bh[t], bn[t], (uint16_t)kx, (uint16_t)ky);
               else
-                ptx::tma_load_2d(dst, &tmA, &ctl->full[s], kidx * BK, m0 + t * BM);
+                ptx::tma_load_2d_a(dst, &tmA, fb, kcol, m0 + t * BM);
             }
-            if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } } }
-            ptx::tma_load_2d(sb + j * kSubB, &tmB, &ctl->full[s], kidx * BK, n0);
+            ptx::tma_load_2d_a(sb + (uint32_t)(j * kSubB), &tmB, fb, kcol, n0);
           }
+          if (MODE == 1) { cb += BK; if (cb == p.cblocks * BK) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } } }
+          kcol += BK;
         }
+        __syncwarp();
+        if (++s == nstages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread; accumulators rotate through the TMEM ring =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
-      const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
-      uint32_t it = 0, acc_it = 0;
-      bool alive = true;
-      for (int tile = tile0; tile < num_tiles && alive; tile += tile_step, acc_it += mt) {
-        uint32_t d_tmem[MT];
+    // ===== MMA issuer: whole warp walks the loop, one elected lane issues; accumulators rotate through TMEM =====
+    constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
+    const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
+    const uint32_t full_a = ptx::smem_u32(&ctl->full[0]), empty_a = ptx::smem_u32(&ctl->empty[0]);
+    const uint32_t tfull_a = ptx::smem_u32(&ctl->tmem_full[0]), tempty_a = ptx::smem_u32(&ctl->tmem_empty[0]);
+    const uint32_t lo0 = ptx::smem_desc_lo(ptx::smem_u32(smem));
+    const uint32_t nstages = (uint32_t)p.stages;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    uint32_t s = 0, ph = 0, slot = 0, sph = 0;
+    bool alive = true;
+    for (int tile = tile0; tile < num_tiles && alive; tile += tile_step) {
+      uint32_t d_tmem[MT], slots[MT];
 #pragma unroll
-        for (int t = 0; t < mt; ++t) {
-          const uint32_t slot = (acc_it + t) % NACC, sph = ((acc_it + t) / NACC) & 1;
-          if (alive && !ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { tc_fail(4); alive = false; }
-          d_tmem[t] = tmem_base + slot * acc_stride<BN>();
-        }
-        if (!alive) break;
+      for (int t = 0; t < mt; ++t) {
+        if (alive && !ptx::mbar_wait_a(tempty_a + 8u * slot, sph ^ 1u)) { tc_fail(4); alive = false; }
+        d_tmem[t] = tbase + slot * acc_stride<BN>();
+        slots[t] = slot;
+        if (++slot == NACC) { slot = 0; sph ^= 1u; }
+      }
+      if (!alive) break;
+      ptx::tc_fence_after();
+      const int kb0 = (tile / mn_tiles) * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+      uint32_t accf = 0;   // the first MMA of a tile overwrites the accumulator
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (!ptx::mbar_wait_a(full_a + 8u * s, ph)) { tc_fail(2); alive = false; break; }
         ptx::tc_fence_after();
-        const int kb0 = (tile / mn_tiles) * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
-        uint32_t accf = 0;   // the first MMA of a tile overwrites the accumulator
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
+        if (ptx::elect_one_sync()) {
           // descriptor low words; every further operand is a constant (>>4) offset away
-          uint32_t a_lo = ptx::smem_desc_lo(sa);
-          uint32_t b_lo = ptx::smem_desc_lo(sa + p.ksub * mt * kSubA);
+          uint32_t a_lo = lo0 + s * (uint32_t)(kStage >> 4);
+          uint32_t b_lo = a_lo + (uint32_t)((p.ksub * mt * kSubA) >> 4);
           for (int j = 0; j < p.ksub; ++j) {
 #pragma unroll
             for (int k = 0; k < BK / 32; ++k) {
@@ -439,16 +366,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
             a_lo += (uint32_t)((mt * kSubA) >> 4);
             b_lo += (uint32_t)(kSubB >> 4);
           }
-          ptx::tc_commit(&ctl->empty[s]);   // slot reusable once these MMAs have read it
+          ptx::tc_commit_a(empty_a + 8u * s);   // slot reusable once these MMAs have read it
         }
-        if (alive) {
-#pragma unroll
-          for (int t = 0; t < mt; ++t) ptx::tc_commit(&ctl->tmem_full[(acc_it + t) % NACC]);
-        }
+        __syncwarp();
+        if (++s == nstages) { s = 0; ph ^= 1u; }
       }
-      if (!alive)   // unblock the epilogue so that the CTA can exit
-        for (int b = 0; b < (int)NACC; ++b) ptx::mbar_arrive(&ctl->tmem_full[b]);
+      if (alive && ptx::elect_one_sync()) {
+#pragma unroll
+        for (int t = 0; t < mt; ++t) ptx::tc_commit_a(tfull_a + 8u * slots[t]);
+      }
+      __syncwarp();
     }
+    if (!alive && lane == 0)   // unblock the epilogue so that the CTA can exit
+      for (int b = 0; b < (int)NACC; ++b) ptx::mbar_arrive(&ctl->tmem_full[b]);
   } else {
     // ===== epilogue: 8 warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
     const int quad = warp & 3;
@@ -492,7 +422,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(wrow + c0 + 4 * g) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
             }
           }
-          if (p.fused_reduce) splitk_fused_finish<BN>(p, split, mn, m0, n0, et, rcp);
         } else {
           // spatial border class of this output pixel -> row of the zero-point correction table
           const int32_t* corr = nullptr;
@@ -535,12 +464,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
 // 40 KB per 768 tensor clocks (52 B/clk/SM) instead of 28 KB per 384 (73 B/clk/SM) against the measured
 // 46.6 B/clk/SM L2 -> SM ingest (profiles/i8_peak.json). TMEM then holds one accumulator, so the epilogue
 // of a tile no longer overlaps the next tile's MMAs — the host picks BN per plan from a cost model.
+// MT = 2 (BN = 256 only): a pair works on a 512 x 256 tile — two 256-row accumulators that share every weight
+// stage (48 KB per 1024 tensor clocks = 47 B/clk/SM instead of 32 KB per 512 = 64 B/clk/SM). Both accumulators
+// fill TMEM, so again there is no epilogue overlap; worth it when the layer has several waves of tiles (conv2).
 //   full[s]       even CTA only, 1 arrival (its producer, expecting the bytes of BOTH CTAs)
 //   empty[s]      each CTA, 1 arrival (the even CTA's multicast commit)
 //   tmem_full[b]  each CTA, 1 arrival (multicast commit)
-//   tmem_empty[b] even CTA only, 2 * kEpiWarps arrivals (the epilogue warps of both CTAs)
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_constant__ CUtensorMap tmA,
+//   tmem_empty[b] even CTA only, 2 * kEpiWarps2 arrivals (the epilogue warps of both CTAs)
+template <int BN, int MT>
+__global__ void __launch_bounds__(kThreads2, 1) tc_igemm2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -550,8 +482,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
   constexpr int NSPLIT = BN > 256 ? 2 : 1;     // MMAs per K step (UMMA N <= 256)
   constexpr int BNI = BN / NSPLIT;             // N of one MMA instruction
   constexpr int kSubA = BM * BK, kSubBq = (BNI / 2) * BK, kSubBh = NSPLIT * kSubBq;
-  constexpr int kStage = kSubA + kSubBh;
-  constexpr uint32_t NACC = num_acc<BN>();
+  constexpr int kStage = MT * kSubA + kSubBh;   // [MT A sub-tiles][this CTA's weight rows]
+  static_assert(num_acc<BN>() >= (uint32_t)MT, "accumulators of one tile must fit TMEM");
+  constexpr uint32_t NACC = num_acc<BN>() / MT;   // tile slots in TMEM, each MT accumulators of BN columns
+  constexpr uint32_t kSlotCols = MT * acc_stride<BN>();
   TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -569,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
     }
     for (int b = 0; b < (int)NACC; ++b) {
       ptx::mbar_init(&ctl->tmem_full[b], 1);
-      ptx::mbar_init(&ctl->tmem_empty[b], 2 * kEpiWarps);
+      ptx::mbar_init(&ctl->tmem_empty[b], 2 * kEpiWarps2);
     }
     ptx::fence_barrier_init();
   }
@@ -583,62 +517,91 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own 128 rows of A, own half of the weight rows =====
-    if (lane == 0) {
-      uint32_t it = 0;
-      bool alive = true;
-      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step) {
-        const int mtile = min((tile / p.tiles_n) * 2 + crank, p.tiles_m - 1);   // tail: re-load the last tile, stores masked
-        const int m0 = mtile * BM, n0 = (tile % p.tiles_n) * BN;
+    // The WHOLE warp walks the loop (every value below is warp-uniform), one elected lane issues. The ring
+    // cursor advances incrementally: a loop iteration is a few dozen instructions, so the single-thread issue
+    // path is never what bounds a K block (with per-iteration div / mod and per-lane operands it was: ~850 clk).
+    const uint32_t smem_a = ptx::smem_u32(smem);
+    const uint32_t full_a = ptx::smem_u32(&ctl->full[0]), empty_a = ptx::smem_u32(&ctl->empty[0]);
+    const uint32_t nstages = (uint32_t)p.stages;
+    uint32_t s = 0, ph = 0;
+    bool alive = true;
+    for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step) {
+      const int n0 = (tile % p.tiles_n) * BN;
+      int bw[MT], bh[MT], bimg[MT];
+#pragma unroll
+      for (int a = 0; a < MT; ++a) {   // accumulator a of this CTA = M tile (2 * MT) * T + 2 * a + crank
+        // tail: M tiles past the end re-load the last one (their stores are masked)
+        const int m0 = min((tile / p.tiles_n) * (2 * MT) + 2 * a + crank, p.tiles_m - 1) * BM;
         const int q = m0 % p.ow, r = m0 / p.ow;
-        const int bw = q * p.stride_w - p.pad, bh = (r % p.oh) * p.stride_h - p.pad, bimg = r / p.oh;
-        int cb = 0, kx = 0, ky = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
-          if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], 2u * (uint32_t)kStage);
-          uint8_t* sa = smem + (size_t)s * kStage;
-          ptx::tma_load_im2col_4d_2cta(sa, &tmA, &ctl->full[s], cb * BK, bw, bh, bimg, (uint16_t)kx, (uint16_t)ky);
-          if (++cb == p.cblocks) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
+        bw[a] = q * p.stride_w - p.pad; bh[a] = (r % p.oh) * p.stride_h - p.pad; bimg[a] = r / p.oh;
+      }
+      const int wrow = n0 + crank * (BNI / 2);
+      int cb = 0, kx = 0, ky = 0, kcol = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        if (!ptx::mbar_wait_a(empty_a + 8u * s, ph ^ 1u)) { tc_fail(1); alive = false; break; }
+        if (ptx::elect_one_sync()) {
+          const uint32_t fb = full_a + 8u * s;
+          if (leader) ptx::mbar_arrive_expect_tx_a(fb, 2u * (uint32_t)kStage);
+          const uint32_t sa = smem_a + s * (uint32_t)kStage;
+#pragma unroll
+          for (int a = 0; a < MT; ++a)
+            ptx::tma_load_im2col_4d_2cta_a(sa + (uint32_t)(a * kSubA), &tmA, fb, cb, bw[a], bh[a], bimg[a], (uint16_t)kx,
+                                           (uint16_t)ky);
 #pragma unroll
           for (int h = 0; h < NSPLIT; ++h)   // this CTA's half of the weight rows of every N = BNI instruction
-            ptx::tma_load_2d_2cta(sa + kSubA + h * kSubBq, &tmB, &ctl->full[s], kb * BK, n0 + h * BNI + crank * (BNI / 2));
+            ptx::tma_load_2d_2cta_a(sa + (uint32_t)(MT * kSubA + h * kSubBq), &tmB, fb, kcol, wrow + h * BNI);
         }
+        __syncwarp();
+        kcol += BK;
+        cb += BK;
+        if (cb == p.cblocks * BK) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } }
+        if (++s == nstages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread of the even CTA drives the tensor cores of both SMs =====
-    if (lane == 0 && leader) {
+    // ===== MMA issuer: the even CTA's warp 1 drives the tensor cores of both SMs (whole warp walks the
+    // loop, one elected lane issues; descriptors advance by constants) =====
+    if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_i8(2 * BM, BNI);
       const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
-      uint32_t it = 0, acc_it = 0;
+      const uint32_t full_a = ptx::smem_u32(&ctl->full[0]), empty_a = ptx::smem_u32(&ctl->empty[0]);
+      const uint32_t tfull_a = ptx::smem_u32(&ctl->tmem_full[0]), tempty_a = ptx::smem_u32(&ctl->tmem_empty[0]);
+      const uint32_t lo0 = ptx::smem_desc_lo(ptx::smem_u32(smem));
+      const uint32_t nstages = (uint32_t)p.stages;
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t s = 0, ph = 0, slot = 0, sph = 0;
       bool alive = true;
-      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step, ++acc_it) {
-        const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
-        if (!ptx::mbar_wait(&ctl->tmem_empty[slot], sph ^ 1)) { tc_fail(4); alive = false; break; }
+      for (int tile = tile0; tile < mn_tiles && alive; tile += tile_step) {
+        if (!ptx::mbar_wait_a(tempty_a + 8u * slot, sph ^ 1u)) { tc_fail(4); alive = false; break; }
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + slot * acc_stride<BN>();
+        const uint32_t d_tmem = tbase + slot * kSlotCols;
         uint32_t accf = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (!ptx::mbar_wait_a(full_a + 8u * s, ph)) { tc_fail(2); alive = false; break; }
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * kStage);
-          const uint32_t a_lo = ptx::smem_desc_lo(sa), b_lo = ptx::smem_desc_lo(sa + kSubA);
+          if (ptx::elect_one_sync()) {
+            const uint32_t a_lo = lo0 + s * (uint32_t)(kStage >> 4), b_lo = a_lo + (uint32_t)((MT * kSubA) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 32; ++k) {
+            for (int k = 0; k < BK / 32; ++k) {
 #pragma unroll
-            for (int h = 0; h < NSPLIT; ++h)
-              ptx::mma_i8_ss_lohi_2cta(d_tmem + (uint32_t)(h * BNI), a_lo + (uint32_t)((k * 32) >> 4), desc_hi,
-                                       b_lo + (uint32_t)((h * kSubBq + k * 32) >> 4), desc_hi, idesc, accf);
-            accf = 1;
+              for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int h = 0; h < NSPLIT; ++h)
+                  ptx::mma_i8_ss_lohi_2cta(d_tmem + (uint32_t)(a * acc_stride<BN>() + h * BNI),
+                                           a_lo + (uint32_t)((a * kSubA + k * 32) >> 4), desc_hi,
+                                           b_lo + (uint32_t)((h * kSubBq + k * 32) >> 4), desc_hi, idesc, accf);
+              accf = 1;
+            }
+            ptx::tc_commit_2cta_multicast_a(empty_a + 8u * s, 3);   // both CTAs' slots are free once these MMAs have read them
           }
-          ptx::tc_commit_2cta_multicast(&ctl->empty[s], 3);   // both CTAs' slots are free once these MMAs have read them
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1u; }
         }
-        if (alive) ptx::tc_commit_2cta_multicast(&ctl->tmem_full[slot], 3);
+        if (alive && ptx::elect_one_sync()) ptx::tc_commit_2cta_multicast_a(tfull_a + 8u * slot, 3);
+        __syncwarp();
+        if (++slot == NACC) { slot = 0; sph ^= 1u; }
       }
-      if (!alive)   // unblock both epilogues so that the CTAs can exit
+      if (!alive && lane == 0)   // unblock both epilogues so that the CTAs can exit
         for (int b = 0; b < (int)NACC; ++b) { ptx::mbar_arrive(&ctl->tmem_full[b]); ptx::mbar_arrive_remote(&ctl->tmem_full[b], 1); }
     }
   } else {
@@ -649,35 +612,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm2_kernel(const __grid_con
     uint32_t tcount = 0, acc_it = 0;
     for (int tile = tile0; tile < mn_tiles; tile += tile_step, ++tcount, ++acc_it) {
       const uint32_t ob = tcount & 1;
-      const int mtile = (tile / p.tiles_n) * 2 + crank;
-      const bool tile_valid = mtile < p.tiles_m;
-      const int m0 = min(mtile, p.tiles_m - 1) * BM, n0 = (tile % p.tiles_n) * BN;
-      for (int j = et; j < BN; j += 32 * kEpiWarps) {
+      const int n0 = (tile % p.tiles_n) * BN;
+      for (int j = et; j < BN; j += 32 * kEpiWarps2) {
         const int n = n0 + j;
         ctl->oc[ob][j] = (n < p.N) ? __ldg(p.ep.oc + n) : 0;
         ctl->bias[ob][j] = 0.f;
         if (p.ep.sb_vec) ctl->sbv[ob][j] = (n < p.N) ? __ldg(p.ep.sb_vec + n) : 1.f;
       }
-      epi_bar_sync();
+      epi_bar_sync2();
       const uint32_t slot = acc_it % NACC, sph = (acc_it / NACC) & 1;
-      const int m = m0 + quad * 32 + lane;
-      const uint32_t t_row = tmem_base + slot * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
-      const int32_t* corr = nullptr;
-      if (p.border_tab && m < p.M) {
-        const int q = m % p.ow, pr = (m / p.ow) % p.oh;
-        const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
-        const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
-        const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
-        const int d = p.pad + 1;
-        const int cls = ((th * d + bh) * d + tw) * d + bw;
-        if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
-      }
       const bool ok = ptx::mbar_wait(&ctl->tmem_full[slot], sph);
       if (!ok) tc_fail(3);
       ptx::tc_fence_after();
-      epilogue_row<BN>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
-                       ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2,
-                       p.ep.sb_vec ? ptx::smem_u32(ctl->sbv[ob]) : 0u);
+#pragma unroll 1
+      for (int a = 0; a < MT; ++a) {
+        const int mtile = (tile / p.tiles_n) * (2 * MT) + 2 * a + crank;
+        const bool tile_valid = mtile < p.tiles_m;
+        const int m = min(mtile, p.tiles_m - 1) * BM + quad * 32 + lane;
+        const uint32_t t_row = tmem_base + slot * kSlotCols + (uint32_t)a * acc_stride<BN>() + ((uint32_t)(quad * 32) << 16);
+        const int32_t* corr = nullptr;
+        if (p.border_tab && m < p.M) {
+          const int q = m % p.ow, pr = (m / p.ow) % p.oh;
+          const int y0 = pr * p.stride_h - p.pad, x0 = q * p.stride_w - p.pad;
+          const int th = min(max(-y0, 0), p.kh), bh = min(max(y0 + p.kh - p.H, 0), p.kh);
+          const int tw = min(max(-x0, 0), p.kw), bw = min(max(x0 + p.kw - p.W, 0), p.kw);
+          const int d = p.pad + 1;
+          const int cls = ((th * d + bh) * d + tw) * d + bw;
+          if (cls != 0) corr = p.border_tab + (size_t)cls * ((p.N + 31) & ~31);
+        }
+        epilogue_row<BN, kEpiWarps2 / 4>(p, t_row, (m < p.M && ok && tile_valid) ? (long long)m : -1ll, n0, ptx::smem_u32(ctl->oc[ob]),
+                         ptx::smem_u32(ctl->bias[ob]), corr, rcp, (warp - 2) >> 2,
+                         p.ep.sb_vec ? ptx::smem_u32(ctl->sbv[ob]) : 0u);
+      }
       // hand the accumulator buffer (both halves) back to the even CTA's MMA warp
       ptx::tc_fence_before();
       __syncwarp();
@@ -1356,9 +1322,6 @@ __global__ void __launch_bounds__(256) fc_splitk_reduce_kernel(const int32_t* __
 std::mutex g_ws_mu;
 int32_t* g_ws = nullptr;
 size_t g_ws_bytes = 0;
-// the last kSkCounterBytes of the scratch allocation hold the fused split-K counters (zero whenever no
-// fc kernel is running: the kernels re-arm them)
-constexpr int kSkCounterBytes = 4096;
 
 int ensure_workspace(size_t bytes, cudaStream_t stream, int32_t** out) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
@@ -1372,7 +1335,6 @@ int ensure_workspace(size_t bytes, cudaStream_t stream, int32_t** out) {
     g_ws = nullptr; g_ws_bytes = 0;
     const size_t want = ((bytes + (bytes >> 2)) + 255) & ~size_t(255);
     I8IE_CUDA_OK(cudaMalloc(&g_ws, want));
-    I8IE_CUDA_OK(cudaMemset(reinterpret_cast<uint8_t*>(g_ws) + want - kSkCounterBytes, 0, kSkCounterBytes));
     g_ws_bytes = want;
   }
   *out = g_ws;
@@ -1444,23 +1406,6 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (p.fused_reduce) {
-    // the sibling CTAs of a tile wait for one another: all of them must be resident at once
-    I8IE_REQUIRE(tiles == grid, "tcgen05 fc: fused split-K needs one tile per CTA (%d tiles, %d SMs)", tiles, num_sms());
-    // Co-residency: one CTA per SM (shared memory) and grid <= SM count, so on a stream that has the GPU to
-    // itself every CTA is resident. I8IE_FC_COOP=1 asks the driver to guarantee it (cooperative launch:
-    // measured ~3 us slower per launch on B200, hence opt-in); a CTA that never sees its siblings times out
-    // and reports role 8 instead of hanging.
-    static const bool coop = std::getenv("I8IE_FC_COOP") != nullptr;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
-    return check_launch("tc_igemm_kernel (fused split-K)");
-  }
   launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
@@ -1468,7 +1413,7 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
 template <int BN, int BK, int MODE>
 int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
   constexpr int kMaxSmem = 227 * 1024;
-  constexpr bool kHasMT2 = (MODE == 1 && BN >= 128);   // 256-row CTA tiles: conv with wide N tiles only
+  constexpr bool kHasMT2 = false;   // 256-row single-CTA tiles: superseded by the CTA-pair kernel, not instantiated
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
   if (p.mt < 1 || !kHasMT2) p.mt = 1;
   if (p.mt == 2) {
@@ -1524,23 +1469,23 @@ int launch_bk(int bk, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, co
   return I8IE_EINVAL;
 }
 
-// CTA-pair launch (see tc_igemm2_kernel): BK = 128, one K block per stage, 128-row tiles
-template <int BN>
+// CTA-pair launch (see tc_igemm2_kernel): BK = 128, one K block per stage, MT 256-row accumulators per tile
+template <int BN, int MT = 1>
 int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
   constexpr int kMaxSmem = 227 * 1024;
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
-  const int kStage = BM * 128 + (BN / 2) * 128;
+  const int kStage = MT * BM * 128 + (BN / 2) * 128;
   int stages = (kMaxSmem - 1024 - ctl_bytes) / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
   I8IE_REQUIRE(stages >= 3, "tcgen05 pair: no room for a pipeline");
   p.stages = stages;
   const int smem = stages * kStage + ctl_bytes + 1024;
-  p.mt = 1; p.splits = 1; p.kb_per = p.num_kb;
+  p.mt = MT; p.splits = 1; p.kb_per = p.num_kb;
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.out_cp + BN - 1) / BN;
-  p.tiles_mp = (p.tiles_m + 1) / 2;
+  p.tiles_mp = (p.tiles_m + 2 * MT - 1) / (2 * MT);
   static int attr_smem = 0;
-  auto kern = tc_igemm2_kernel<BN>;
+  auto kern = tc_igemm2_kernel<BN, MT>;
   if (attr_smem < smem) {
     I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
@@ -1548,7 +1493,7 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, c
   const int tiles = p.tiles_mp * p.tiles_n;
   const int max_clusters = num_sms() / 2;
   const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
-  launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
+  launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads2), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm2_kernel");
 }
 
@@ -1677,7 +1622,7 @@ int tc_pick_bn(int n) { return pick_bn(n); }
 // then holds bn / 2 rows = whole 1 KB swizzle atoms). I8IE_NO_CLUSTER=1 forces single CTAs (tests).
 int tc_conv_cluster(int bk, int bn) {
   if (std::getenv("I8IE_NO_CLUSTER") != nullptr) return 1;
-  const bool ok = bk == 128 && (bn == 384 || bn == 256 || bn == 192 || bn == 128);
+  const bool ok = bk == 128 && (bn == 256 || bn == 192 || bn == 128);
   return ok ? 2 : 1;
 }
 
@@ -1685,37 +1630,21 @@ int tc_conv_cluster(int bk, int bn) {
 // MMA instruction (N <= 256 per instruction; BN = 384 is two instructions of N = 192).
 int tc_pair_box_rows(int bn) { return bn > 256 ? bn / 4 : bn / 2; }
 
-// N tile of a conv plan served by the pair kernel. Cost model per candidate (clocks, one SM pair):
-//   tile  = K blocks x max(tensor clocks, L2 ingest clocks)      tensor: 2 * BN per 128-byte K block;
-//           ingest: (16 KB of A + 64 * BN bytes of weights) at ~40 B/clk/SM (85 % of the measured 46.6)
-//   total = waves over the 74 SM pairs x tile  (+ the exposed epilogue of the single-accumulator BN = 384
-//           variant for every further tile of a pair)
-// The widest tile wins when the work is a single wave (batch 100: conv3/conv4 in one wave of 256 x 384 tiles
-// instead of two waves of 256 x 192); at other batch sizes wave quantisation decides.
-int tc_pick_bn_pair(const GemmGeom& g, int bk) {
-  const int base = pick_bn(g.out_cp);
-  if (const char* e = std::getenv("I8IE_TC_BN"))   // dev / test override (384 only where it tiles the channels)
-    return (std::atoi(e) == 384 && bk == 128 && g.out_cp % 384 == 0 && std::getenv("I8IE_NO_CLUSTER") == nullptr) ? 384 : base;
-  if (bk != 128 || std::getenv("I8IE_NO_CLUSTER") != nullptr) return base;
-  const int pairs = std::max(1, num_sms() / 2);
-  const long long num_kb = (long long)g.kh * g.kw * (g.cp / 128);
-  const long long tiles_m = ((g.M + BM - 1) / BM + 1) / 2;
-  int best = base;
-  long long best_cost = -1;
-  for (int bn : {384, 256, 192, 128}) {
-    if (bn > 256 && g.out_cp % bn != 0) continue;        // 384 only when it tiles the channels exactly
-    if (bn > g.out_cp && bn != base) continue;
-    const long long tiles = tiles_m * ((g.out_cp + bn - 1) / bn);
-    const long long waves = (tiles + pairs - 1) / pairs;
-    const long long tile = num_kb * std::max<long long>(2 * bn, (16384 + 64 * bn) / 40);
-    const long long cost = waves * tile + (bn > 256 ? (waves - 1) * (bn / 64) * 350 : 0);
-    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
-  }
-  return best;
+// N tile (and accumulators per tile) of a conv plan served by the pair kernel: the narrowest tile that
+// covers the output pitch with the fewest padded columns (pick_bn), one 256-row accumulator per tile.
+// Measured on B200 with 16 epilogue warps (profiles/r02_pair_tile_ab.md, AlexNet conv2-5, batch 100-1000):
+// this beats both wide variants the kernel template can express — a 384-column tile (two N = 192 MMAs per A
+// stage) and 512 x 256 tiles (two accumulators per weight stage) cut the L2 -> SM bytes per MAC by 19-25 %,
+// but fill TMEM with ONE tile, and the lost epilogue / main-loop overlap costs more (conv4 batch 250:
+// 59.5 us vs 39.1 us) — so they are not instantiated. I8IE_TC_BN overrides the width (tests).
+int tc_pick_bn_pair(const GemmGeom& g, int bk, int* mt_out) {
+  (void)bk;
+  *mt_out = 1;
+  return pick_bn(g.out_cp);
 }
 
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
-                   const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream) {
+                   const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream, int pair_mt) {
   TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.cblocks = g.cp / bk;
@@ -1726,11 +1655,11 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
   p.fast_requant = requant_fast_ok(ep);
   if (cluster == 2) {   // CTA pairs
     I8IE_REQUIRE(bk == 128, "tcgen05 pair: needs 128-byte K blocks");
+    (void)pair_mt;
     switch (bn) {
       case 128: return launch_pair_bn<128>(tmA, tmB, p, stream);
       case 192: return launch_pair_bn<192>(tmA, tmB, p, stream);
       case 256: return launch_pair_bn<256>(tmA, tmB, p, stream);
-      case 384: return launch_pair_bn<384>(tmA, tmB, p, stream);
     }
     set_error("tcgen05 pair: unsupported BN %d", bn);
     return I8IE_EINVAL;
@@ -1776,24 +1705,12 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   p.kh = p.kw = 1; p.stride_h = p.stride_w = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep);
-  // weights are read once per launch: a stream from DRAM whenever the batch is small
-  static const bool pf_ok = [] { const char* e = std::getenv("I8IE_FC_PREFETCH"); return !(e && e[0] == '0'); }();
-  p.pf_weights = (pf_ok && m <= 1024) ? 1 : 0;
   if (splits <= 1) return launch_bk<0>(128, bn, tmA, tmB, p, stream);
   // split K across CTAs, then fold the partial sums (exact: integer adds commute)
   p.splits = splits; p.kb_per = kb_per;
   p.ws_ld = ((ldy + bn - 1) / bn) * bn;
-  const int mn_tiles = ((m + BM - 1) / BM) * ((ldy + bn - 1) / bn);
-  const size_t part_bytes = (sizeof(int32_t) * (size_t)p.splits * m * p.ws_ld + 255) & ~size_t(255);
-  int rc = ensure_workspace(part_bytes + kSkCounterBytes, stream, &p.ws);
+  int rc = ensure_workspace(sizeof(int32_t) * (size_t)p.splits * m * p.ws_ld, stream, &p.ws);
   if (rc != I8IE_OK) return rc;
-  // one kernel when every (split, tile) gets its own co-resident CTA; I8IE_FC_FUSED=0 keeps the two-kernel path
-  static const bool fused_ok = [] { const char* e = std::getenv("I8IE_FC_FUSED"); return e && e[0] == '1'; }();
-  if (fused_ok && mn_tiles * p.splits <= num_sms() && 2 * mn_tiles * (int)sizeof(unsigned) <= kSkCounterBytes) {
-    p.fused_reduce = 1;
-    p.sk_counters = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(g_ws) + g_ws_bytes - kSkCounterBytes);
-    return launch_bk<0>(128, bn, tmA, tmB, p, stream);
-  }
   rc = launch_bk<0>(128, bn, tmA, tmB, p, stream);
   if (rc != I8IE_OK) return rc;
   const long long threads = (long long)m * (ldy / 4);

@@ -244,10 +244,13 @@ class ShardedStep:
     model     an i8ie.Module (converted); its own graph replay is bypassed (the forward is captured here)
     inputs    list of i8ie.Tensor device batches [rows, ...] (static buffers: replays read them in place)
     ref_args  list of int64 CUDA tensors [rows] (reference argmax per input) or None
-    exchange  PeerExchange (or ResultExchange: NCCL inside the capture)"""
+    exchange  PeerExchange (captured with the forward). With a ResultExchange (NCCL) only the forward is
+              captured and the exchange is enqueued after every replay: an NCCL collective inside the
+              capture hung on the B200 box (torch 2.11 / NCCL 2.28), so it is not attempted."""
 
     def __init__(self, model, inputs, ref_args, exchange):
         self.model, self.inputs, self.exchange = model, list(inputs), exchange
+        self.in_graph = isinstance(exchange, PeerExchange)
         self.ref_args = list(ref_args) if ref_args is not None else [None] * len(self.inputs)
         self.graphs = []
         self.kernels_per_step = 0
@@ -267,7 +270,8 @@ class ShardedStep:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
                     out = model(x)
-                    exchange(out.data.buf.view(rows, cols), ref)
+                    if self.in_graph:
+                        exchange(out.data.buf.view(rows, cols), ref)
                 self.kernels_per_step = int(_lib.launch_count() - before)
                 pool = pool or g.pool()
                 self.graphs.append((g, out))
@@ -277,8 +281,11 @@ class ShardedStep:
     def __call__(self, i: int):
         """Runs step i (input i modulo the ring). Returns the exchange's static result buffers
         (logits of all ranks, agreement count), valid until the next step."""
-        self.graphs[i % len(self.graphs)][0].replay()
+        j = i % len(self.graphs)
+        self.graphs[j][0].replay()
         self.replays += 1
+        if not self.in_graph:
+            self.exchange(self.graphs[j][1].data.buf.view(self.exchange.rows, self.exchange.cols), self.ref_args[j])
         return self.exchange.logits_all, self.exchange.agree
 
     def local_logits(self, i: int):

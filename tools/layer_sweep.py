@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE config 5: every AlexNet conv / fc layer standalone (u8 activations U{0..255}, s8 weights),
 batch 1 .. 4096, as TOP/s on the reference's un-padded dims next to the INT8 tensor roofline
-(2 x the measured cuBLAS bf16 rate of MEASURED_PEAKS.json). Writes a markdown table to stdout."""
+(the measured kind::i8 peak of profiles/i8_peak.json, else 2 x the measured cuBLAS bf16 rate). Writes a markdown table to stdout."""
 import argparse
 import json
 import os
@@ -21,6 +21,11 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     bf16 = json.load(open(pk))["bf16_tflops"] if os.path.exists(pk) else 1590.0
     peak = 2 * bf16
+    pi8 = os.path.join(ROOT, "profiles", "i8_peak.json")
+    peak_src = f"2 x measured bf16 {bf16} TFLOP/s"
+    if os.path.exists(pi8):   # kind::i8 tensor peak measured with the UTCIMMA-only microbenchmark
+        peak = json.load(open(pi8))["i8_tops_burst"]
+        peak_src = "measured kind::i8 peak, tools/ubench/i8_peak.cu"
     batches = [int(b) for b in args.batches.split(",")]
     table = {}
     names = []
@@ -32,7 +37,7 @@ def main():
                 names.append(name)
         print(f"# batch {b} done", file=sys.stderr, flush=True)
     print(f"# AlexNet layer sweep on one B200: TOP/s (un-padded 2*M*N*K) / % of {peak:.0f} TOP/s "
-          f"(2 x measured bf16 {bf16} TFLOP/s) / us per launch")
+          f"({peak_src}) / us per launch")
     print("| batch | " + " | ".join(names) + " |")
     print("|---|" + "---|" * len(names))
     for b in batches:
