@@ -66,6 +66,21 @@ def _act_pitch(c):
     return (c + 31) // 32 * 32
 
 
+_SLACK = 128
+
+
+def _u8_empty(numel, device):
+    """u8 activation buffer of exactly `numel` bytes with >= 128 readable bytes behind it in the same
+    allocation: a row-mode convolution's last K block reads a few bytes past the last pixel (against
+    zero weights), which must stay inside mapped memory."""
+    return torch.empty(int(numel) + _SLACK, dtype=torch.uint8, device=device)[:int(numel)]
+
+
+def _has_slack(t):
+    st = t.untyped_storage()
+    return st.nbytes() - (t.storage_offset() + t.numel()) * t.element_size() >= _SLACK
+
+
 def _need_cuda():
     if not torch.cuda.is_available():
         raise I8ieError("no CUDA device visible: the i8ie B200 backend has no CPU fallback")
@@ -459,6 +474,9 @@ class TensorU8(_TensorBase):
             out = pool.launch_padded(cpx, pad, self._zp)
         else:
             buf, cp = self._as_nhwc(n, c, h, w)
+            if pad == 0 and cp == cpx and _has_slack(buf):
+                cache[(cpx, pad)] = buf      # no border to add: the NHWC tensor is already the operand
+                return buf
             out = torch.empty(n * (h + 2 * pad) * (w + 2 * pad) * cpx + 128, dtype=torch.uint8, device=buf.device)
             check(L.i8ie_maxpool_u8_nhwc_padded(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, 1, 1, cpx, pad,
                                                 self._zp, _stream()), "u8_nhwc pad-copy")
@@ -476,7 +494,7 @@ class TensorU8(_TensorBase):
             return self._st.t, cp
         L = _need_cuda()
         src = self._dense_buf()
-        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=src.device)
+        out = _u8_empty(n * h * w * cp, src.device)
         check(L.i8ie_u8_nchw_to_nhwc(src.data_ptr(), out.data_ptr(), n, c, h, w, cp, self._zp, _stream()),
               "u8_nchw_to_nhwc")
         return out, cp
@@ -513,7 +531,7 @@ class _DeferredPool:
         n, c, h, w = x._shape
         oh, ow = (h - k) // s + 1, (w - k) // s + 1
         buf, cp = x._as_nhwc(n, c, h, w)
-        out = torch.empty(n * oh * ow * (c if self.out_nchw else cp), dtype=torch.uint8, device=buf.device)
+        out = _u8_empty(n * oh * ow * (c if self.out_nchw else cp), buf.device)
         check(L.i8ie_maxpool_u8_nhwc(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, k, s,
                                      1 if self.out_nchw else 0, _stream()), "maxpool_u8_nhwc")
         if self.out_nchw:
@@ -546,7 +564,7 @@ class _DeferredQuant:
         L = _need_cuda()
         n, c, h, w, cp = self.geom
         ptr, slot, dev = _src_ptrs(self.src)
-        out = torch.empty(n * h * w * cp, dtype=torch.uint8, device=dev)
+        out = _u8_empty(n * h * w * cp, dev)
         if slot is not None:
             check(L.i8ie_quantize_nchw_f32_nhwc_u8_indirect(slot, out.data_ptr(), n, c, h, w, cp, self.scale,
                                                             self.zp, _stream()), "quantize_nchw_f32_nhwc_u8_indirect")
@@ -1085,7 +1103,7 @@ class Conv2d(_BaseLayer):
             cpx = _r16(c)
         if cpx:
             xp = x._as_padded_nhwc(n, c, h, w, cpx, self._pad)
-            out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=xp.device)
+            out = _u8_empty(n * oh * ow * out_cp, xp.device)
             plan = self._plan(n, c, h, w, cpx, 4)
             self._last_impl = 4
             check(L.i8ie_conv2d_u8(plan, xp.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
@@ -1093,7 +1111,7 @@ class Conv2d(_BaseLayer):
                                    acc_out.data_ptr() if acc_out is not None else None, _stream()), "conv2d_u8 (row mode)")
             return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
         buf, cp = x._as_nhwc(n, c, h, w)
-        out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=buf.device)
+        out = _u8_empty(n * oh * ow * out_cp, buf.device)
         plan = self._plan(n, c, h, w, cp, impl)
         self._last_impl = int(L.i8ie_conv2d_plan_impl(plan))   # 1 SIMT, 2 tcgen05 im2col, 3 tcgen05 stem
         flags = 1 if relu else 0
@@ -1122,7 +1140,7 @@ class Conv2d(_BaseLayer):
         oc, _ = self._offsets(int(in_zp), in_scale, True)
         out_cp = _act_pitch(kc)
         ptr, slot, dev = _src_ptrs(x)
-        out = torch.empty(n * oh * ow * out_cp, dtype=torch.uint8, device=dev)
+        out = _u8_empty(n * oh * ow * out_cp, dev)
         flags = 1 if (self.fuse_relu if relu is None else relu) else 0
         fn = L.i8ie_conv2d_f32_u8_indirect if slot is not None else L.i8ie_conv2d_f32_u8
         check(fn(plan, slot if slot is not None else ptr, in_scale, int(in_zp), out.data_ptr(), oc.data_ptr(),

@@ -141,8 +141,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
     p->bn = tc_pick_bn_pair(p->gv, 128, &p->pair_mt);
     p->cluster = tc_conv_cluster(128, p->bn);
     int rc4 = I8IE_OK;
-    if (p->cluster != 2) { set_error("conv2d_plan_create: row mode needs the pair kernel (bn=%d)", p->bn); rc4 = I8IE_EINVAL; }
-    if (rc4 == I8IE_OK && cudaMalloc(&p->row_w, (size_t)kc_pad * kh * p->kr) != cudaSuccess) {
+    if (cudaMalloc(&p->row_w, (size_t)kc_pad * kh * p->kr) != cudaSuccess) {
       set_error("conv2d_plan_create: cudaMalloc of the row-mode weights failed");
       rc4 = I8IE_ECUDA;
     }
@@ -152,7 +151,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
       rc4 = I8IE_ECUDA;
     }
     if (rc4 == I8IE_OK)
-      rc4 = tc_encode_weight_map(&p->tmB, p->row_w, kc_pad, kh * p->kr, 128, tc_pair_box_rows(p->bn));
+      rc4 = tc_encode_weight_map(&p->tmB, p->row_w, kc_pad, kh * p->kr, 128, p->cluster > 1 ? tc_pair_box_rows(p->bn) : p->bn);
     if (rc4 != I8IE_OK) { plan_free(p); return nullptr; }
     return p;
   }
@@ -257,8 +256,8 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
     int rc = plan->amaps.get(x, 4, 0, 0, 0, &tmA,
                              [&](CUtensorMap* m) { return tc_encode_act_map_row_mode(m, x, plan->g, plan->kr); });
     if (rc != I8IE_OK) return rc;
-    return launch_tc_conv(plan->gv, tmA, plan->tmB, 128, plan->bn, 2, nullptr, y, ep, zp_in, (cudaStream_t)stream,
-                          plan->pair_mt);
+    return launch_tc_conv(plan->gv, tmA, plan->tmB, 128, plan->bn, plan->cluster, nullptr, y, ep, zp_in,
+                          (cudaStream_t)stream, plan->pair_mt);
   }
   if (plan->impl == 2) {
     CUtensorMap tmA;

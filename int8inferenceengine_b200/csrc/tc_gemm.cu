@@ -75,12 +75,13 @@ struct TcParams {
 namespace {
 
 constexpr int BM = 128;
-constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant (warp % 4), alternating 32-column chunks
+// Four epilogue warps per TMEM lane quadrant (warp % 4), taking every fourth 32-column chunk. One 32 x 32
+// chunk costs a warp ~1000 clk (TMEM load, ~250 dependent-ish instructions, two stores): with 8 warps the
+// epilogue of a 128 x 256 tile (4000 clk) held its accumulator long enough to stall the MMA issuer and left a
+// 2 us tail per launch; 16 warps took AlexNet conv2 at batch 100 from 40 to 32 us.
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
-// Pair kernel: four epilogue warps per TMEM lane quadrant. One 32 x 32 chunk costs a warp ~1000 clk (TMEM load,
-// ~250 dependent-ish instructions, two stores), and with the wide single-accumulator tiles (BN = 384, 512 x 256)
-// the epilogue of a tile is exposed: 16 warps halve it (and the tail of every launch).
-constexpr int kEpiWarps2 = 16;
+constexpr int kEpiWarps2 = kEpiWarps;   // (pair kernel: same count)
 constexpr int kThreads2 = 64 + 32 * kEpiWarps2;
 __device__ __forceinline__ void epi_bar_sync2() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps2) : "memory"); }
 // stem kernel: its K is tiny (22 MMAs per tile), so the fp32 epilogue is the longest stage; with two
@@ -129,7 +130,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 
 // One output row (= one TMEM lane) of a 128 x BN accumulator tile: + oc, [border correction],
 // [fc float bias], requantise, [relu], packed u8 store. m < 0: row is padding (nothing stored).
-// Two warps share each TMEM lane quadrant and take alternate 32-column chunks (`half`).
+// NSUB warps share each TMEM lane quadrant; warp `half` of them takes the chunks half, half + NSUB, ...
 // `s_oc` / `s_bias` are shared-memory addresses of this tile's staged per-channel terms.
 template <int BN, int NSUB = kEpiWarps / 4>   // NSUB warps share a quadrant and take every NSUB-th chunk
 __device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t t_row, long long m, int n0,
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
     if (!alive && lane == 0)   // unblock the epilogue so that the CTA can exit
       for (int b = 0; b < (int)NACC; ++b) ptx::mbar_arrive(&ctl->tmem_full[b]);
   } else {
-    // ===== epilogue: 8 warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
+    // ===== epilogue: kEpiWarps warps, warp w owns TMEM lanes [32*(w%4), +32) = output rows =====
     const int quad = warp & 3;
     const int et = threadIdx.x - 64;
     const float rcp = __frcp_rn(p.ep.sc);
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
           ptx::tc_fence_after();
           int32_t* wrow = p.ws + ((size_t)split * p.M + (m < p.M ? m : 0)) * p.ws_ld + n0;
 #pragma unroll 1
-          for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 64) {
+          for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
@@ -814,6 +815,17 @@ __device__ __forceinline__ void stem_trace(const Stem2Params& sp, uint32_t it, i
   if (sp.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceTiles) sp.trace[it * kTraceEvents + ev] = clock64();
 }
 
+// Per-role tile / ring cursors of the stem kernel, advanced incrementally: every role used to divide the
+// tile index by `pairs` and the tile counter by the ring depths once per tile (runtime divisors: ~25
+// instructions each through the slow conversion pipes), ~150 instructions per warp per tile x 22 warps.
+struct StemCursor {
+  int img, pr;          // image, output-row pair within the image
+  uint32_t s, ph;       // ring slot and phase bit
+  __device__ __forceinline__ void init(int tile, int pairs) { img = tile / pairs; pr = tile - img * pairs; s = 0; ph = 0; }
+  __device__ __forceinline__ void next_tile(int pairs) { if (++pr == pairs) { pr = 0; ++img; } }
+  __device__ __forceinline__ void next_slot(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
 // FQ: the input quantise is fused. Warp 0 bulk-copies the raw fp32 image rows of a tile
 // (cp.async.bulk, one row of one channel plane per copy) into a second shared-memory ring, 8
 // converter warps quantise them into superpixel rows of the operand ring (generic-proxy stores +
@@ -903,10 +915,11 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
           ptx::prefetch_l2_bulk(xf + (((int64_t)pimg * sp.c + lane) * sp.h + (pr0 + plo)) * sp.w, (uint32_t)(phi - plo) * frow_bytes);
       };
       for (int t = t_begin; t < t_begin + pf_ahead; ++t) prefetch_tile(t);
-      for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
-        const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
-        const uint32_t s = it % (uint32_t)sp.f_stages;
-        const uint32_t ph = (it / (uint32_t)sp.f_stages) & 1;
+      StemCursor cur;
+      cur.init(t_begin, sp.pairs);
+      for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it, cur.next_tile(sp.pairs), cur.next_slot((uint32_t)sp.f_stages)) {
+        const int img = cur.img, p0 = cur.pr * 2;
+        const uint32_t s = cur.s, ph = cur.ph;
         if (pf_ahead > 0) prefetch_tile(tile + pf_ahead);
         if (!ptx::mbar_wait(&f_empty[s], ph ^ 1)) { tc_fail(1); alive = false; break; }
         if (lane == 0) stem_trace(sp, it, 0);
@@ -961,10 +974,12 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     bool alive = ptx::mbar_wait(w_full, 0);
     if (!alive) tc_fail(5);
     uint32_t it = 0;
+    StemCursor mcur;
+    mcur.s = 0; mcur.ph = 0;
     for (int tile = t_begin; tile < t_end && alive; tile += t_step, ++it) {
       const uint32_t buf = it & 1, bph = (it >> 1) & 1;
-      const uint32_t s = it % (uint32_t)sp.stages;
-      const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
+      const uint32_t s = mcur.s, ph = mcur.ph;
+      mcur.next_slot((uint32_t)sp.stages);
       if (!ptx::mbar_wait(&ctl->tmem_empty[buf], bph ^ 1)) { tc_fail(4); alive = false; break; }
       if (lane == 0) stem_trace(sp, it, 8);
       if (!ptx::mbar_wait(&ctl->full[s], ph)) { tc_fail(2); alive = false; break; }
@@ -1027,12 +1042,16 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     }
     uint32_t it = 0;
     bool dead = false;
-    for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
-      const int p0 = (tile % sp.pairs) * 2;
-      const uint32_t s = it % (uint32_t)sp.stages;
-      const uint32_t ph = (it / (uint32_t)sp.stages) & 1;
-      const uint32_t fs = it % (uint32_t)sp.f_stages;
-      const uint32_t fph = (it / (uint32_t)sp.f_stages) & 1;
+    StemCursor ccur, fcur;
+    ccur.init(t_begin, sp.pairs);
+    fcur.s = 0; fcur.ph = 0;
+    uint32_t sprev_slot = 0;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++it, ccur.next_tile(sp.pairs)) {
+      const int p0 = ccur.pr * 2;
+      const uint32_t s = ccur.s, ph = ccur.ph;
+      const uint32_t fs = fcur.s, fph = fcur.ph;
+      ccur.next_slot((uint32_t)sp.stages);
+      fcur.next_slot((uint32_t)sp.f_stages);
       const int i0 = 4 * p0;
       int nrows = sp.hp - i0;
       if (nrows > rows_per_tile) nrows = rows_per_tile;
@@ -1051,7 +1070,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       int i_start = 0;
       if (!first) {
         // tile row i is row i + 8 of the previous tile: same region (i & 3), two 1 KB slots further on
-        const uint32_t sprev = sA_u + ((it - 1) % (uint32_t)sp.stages) * (uint32_t)a_stage;
+        const uint32_t sprev = sA_u + sprev_slot * (uint32_t)a_stage;
         for (int i = pw; i < i_new; i += kProdW) {
           const uint32_t off = (uint32_t)((i & 3) * sp.nsl + (i >> 2)) * 1024u;
 #pragma unroll
@@ -1126,6 +1145,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         ptx::mbar_arrive(&f_empty[fs]);
       }
       if (pw == 0 && lane == 0) stem_trace(sp, it, 6);
+      sprev_slot = s;
     }
   } else {
     const int quad = warp & 3;
@@ -1139,9 +1159,13 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiW) : "memory");
     uint32_t it = 0;
+    StemCursor ecur;
+    ecur.init(t_begin, sp.pairs);
     for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
       const uint32_t buf = it & 1, bph = (it >> 1) & 1;
-      const int img = tile / sp.pairs, p0 = (tile % sp.pairs) * 2;
+      // FQ: contiguous tile run (cursor); otherwise tiles are strided over the grid
+      const int img = FQ ? ecur.img : tile / sp.pairs, p0 = (FQ ? ecur.pr : tile % sp.pairs) * 2;
+      if (FQ) ecur.next_tile(sp.pairs);
       const int l = quad * 32 + lane;            // TMEM lane = tile row
       const int prow = p0 + (l >> 6), q = l & 63;
       const bool valid = (prow < sp.oh) && (q < sp.ow);
@@ -1562,20 +1586,24 @@ int tc_encode_act_map_im2col(CUtensorMap* tm, const uint8_t* x, const GemmGeom& 
 // ---- row mode host side (see row_weight_kernel) ----
 int tc_row_mode_kr(int cpx, int kw) { return (kw * cpx + 127) / 128 * 128; }
 
-// Hard constraints of row mode: stride 1, the pair kernel's wide N tiles, a run that fits a few K blocks.
+// Hard constraints of row mode: stride 1, a run that fits a few K blocks.
 bool tc_row_mode_ok(int c, int kh, int kw, int stride, int pad, int out_cp) {
-  if (std::getenv("I8IE_NO_CLUSTER") != nullptr) return false;
-  if (stride != 1 || kw < 2 || pad > 8 || out_cp < 128 || kh > 16) return false;
+  if (stride != 1 || kw < 2 || pad > 8 || out_cp % 16 != 0 || kh > 16) return false;
   return tc_row_mode_kr((c + 15) / 16 * 16, kw) <= 2048;
 }
 
 // Channel pitch (bytes per pixel) the physically padded input must have, or 0 when the layer should
-// stay on the plain im2col path (auto dispatch): row mode must save at least 10 % of the K bytes.
+// stay on the plain im2col path (auto dispatch). Row mode is taken when it saves at least 10 % of the K
+// bytes (C = 96: 5 x 512 instead of 25 x 128), and for narrow-channel layers whose plain path would run
+// K blocks of 16 / 32 / 64 bytes (or the SIMT kernel): there the run of kw pixels is one 128-byte-wide K
+// block per filter row instead of kw small ones, as long as that costs at most 2x the K bytes.
 int tc_row_mode_cp(int c, int cp_plain, int kh, int kw, int stride, int pad, int out_cp) {
   if (std::getenv("I8IE_NO_ROW_MODE") != nullptr || !tc_row_mode_ok(c, kh, kw, stride, pad, out_cp)) return 0;
   const int cpx = (c + 15) / 16 * 16;
-  const long long k_plain = (long long)kh * kw * cp_plain;
-  return (long long)kh * tc_row_mode_kr(cpx, kw) * 10 <= k_plain * 9 ? cpx : 0;
+  const long long k_plain = (long long)kh * kw * cp_plain, k_row = (long long)kh * tc_row_mode_kr(cpx, kw);
+  if (k_row * 10 <= k_plain * 9) return cpx;
+  if (cp_plain % 128 != 0 && k_row <= 2 * k_plain) return cpx;
+  return 0;
 }
 
 int tc_row_pack_weights(const GemmGeom& g, const int8_t* w_packed, int8_t* wr, int kr, cudaStream_t stream) {

@@ -165,6 +165,10 @@ ROW = [  # stride-1 convs whose channel count is not a multiple of 128: row mode
     (2, 160, 9, 9, 256, 3, 1, 0),        # no padding, run 480 -> 512
     (5, 20, 28, 28, 130, 5, 1, 3),       # pad 3, C = 20 -> pitch 32, run 160 -> 256, ragged N
     (2, 200, 11, 7, 384, 2, 1, 1),       # even filter, non-square image, N = 384
+    (7, 3, 32, 32, 20, 5, 1, 0),         # narrow layers on the single-CTA kernel: simple-conv conv1 (pitch 16, no padding:
+    (7, 20, 28, 28, 50, 5, 1, 0),        #   the NHWC tensor itself is the operand), conv2 (pitch 32), conv3 (pitch 64)
+    (7, 50, 12, 12, 120, 5, 1, 0),
+    (3, 1, 28, 28, 20, 5, 1, 2),         # one channel, padded
 ]
 
 
