@@ -267,6 +267,17 @@ I8IE_API int i8ie_fc_u8_pc(const uint8_t* x, int ldx, const int8_t* w, int ldw, 
                            const float* sb_vec, float sb_min, float sb_max, float sc, int zp_out, int flags,
                            int32_t* acc_out, int impl, void* stream);
 
+/* Linear::forward_prop(Tensor<u8>&&) (fully_connected.cc:22-52) of a model's LAST layer together with
+ * Module.__call__'s final dequantize (i8ie/module.py:22-24 -> quantize_utils.cc:54-58 -> :38-42):
+ * y as i8ie_fc_u8 / i8ie_fc_u8_pc (sb_vec may be NULL: per-tensor scale sb), and
+ *   deq_out[m, n] (dense fp32) = ((float)y - zp_out) * sc.
+ * Classifier heads (n_pad == ldy == 16) do both in one kernel; other shapes run the fc kernel and
+ * then the standalone dequantise — same values either way. */
+I8IE_API int i8ie_fc_u8_deq(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+                            int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
+                            const float* sb_vec, float sb_min, float sb_max, float sc, int zp_out, int flags,
+                            int impl, float* deq_out, void* stream);
+
 /* Debug hook (not part of the reference-facing surface): synchronises the device and
  * returns the first protocol error (mbarrier wait timeout) a tensor-core kernel recorded
  * (0 = none, >0 = role that timed out), optionally clearing it; negative on CUDA errors. */

@@ -182,11 +182,11 @@ class Module:
                               "running eagerly")
                 self.graph = False
                 return self._call_eager(x)
-        return Tensor(_B.replay_forward(st, x.data))
+        return Tensor(_B.replay_forward(st, x.data, self._call_eager))
 
     def graph_launches(self):
         """Kernels replayed through CUDA graphs so far (they bypass the C-ABI launch counter)."""
-        return sum(st.get("replays", 0) * st.get("kernels", 0) for st in self.__dict__.get("_graphs", {}).values())
+        return sum(st.get("launched", 0) for st in self.__dict__.get("_graphs", {}).values())
 
     def prepare(self):
         for _, val in self.__dict__.items():

@@ -22,6 +22,7 @@ import ctypes as C
 import os
 import sys
 import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -421,12 +422,14 @@ class TensorU8(_TensorBase):
         # Deferred tensors launch their kernel the first time the bytes are needed. Until then a
         # following relu / flatten / first-layer conv can still fold itself into that launch.
         if self._storage is None:
-            st, layout, geom = self._deferred.launch()
-            self._storage = st
-            st.views += 1
-            self._layout, self._geom = layout, geom
-            self._deferred = None
+            self._resolve(*self._deferred.launch())
         return self._storage
+
+    def _resolve(self, st, layout, geom):
+        self._storage = st
+        st.views += 1
+        self._layout, self._geom = layout, geom
+        self._deferred = None
 
     def _pending(self, kind=None):
         d = self._deferred if self._storage is None else None
@@ -642,6 +645,13 @@ def dequantize(x):
     L = _need_cuda()
     if not isinstance(x, TensorU8):
         raise TypeError("dequantize(): incompatible function arguments (expected a u8 tensor)")
+    pend = x._pending("layer")
+    if pend is not None and isinstance(pend.layer, Linear):
+        # the model's last fc has not been launched yet: one entry point computes the u8 result and its
+        # dequantised copy (classifier heads: in the same kernel)
+        y, out = pend.layer._forward_u8(pend.x, relu=pend.relu or pend.layer.fuse_relu, deq=True)
+        x._resolve(y._st, y._layout, y._geom)
+        return TensorF32(_Storage(out), x._shape)
     numel = int(np.prod(x._shape)) if x._shape else 1
     out = torch.empty(numel, dtype=torch.float32, device=x.buf.device)
     if x._layout == "nhwc" and x._geom[2] * x._geom[3] == 1:
@@ -968,8 +978,9 @@ class Linear(_BaseLayer):
             raise RuntimeError(f"Linear: input has {k} features, weight expects {kw}")
         return [m, n], (m, n, 1, 1, _r16(n))
 
-    def _forward_u8(self, x, acc_out=None, impl=0, relu=None):
+    def _forward_u8(self, x, acc_out=None, impl=0, relu=None, deq=False):
         # Linear::forward_prop(Tensor<u8>&&), fully_connected.cc:22-52
+        # deq=True: also returns the dequantised result [m, n] fp32 (i8ie_fc_u8_deq)
         L = _lib.load()
         self._out_meta(x)
         m, k = x._shape
@@ -979,6 +990,16 @@ class Linear(_BaseLayer):
         ldy = _r16(n)
         out = torch.empty(m * ldy, dtype=torch.uint8, device=buf.device)
         flags = 1 if (self.fuse_relu if relu is None else relu) else 0
+        if deq:
+            pc = getattr(self, "_w_scales_dev", None)
+            f32 = torch.empty(m * n, dtype=torch.float32, device=buf.device)
+            check(L.i8ie_fc_u8_deq(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
+                                   out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
+                                   float(self._w_scale), pc.data_ptr() if pc is not None else None,
+                                   float(self._w_scales.min()) if pc is not None else 0.0,
+                                   float(self._w_scales.max()) if pc is not None else 0.0,
+                                   float(self._scale), self._zp, flags, impl, f32.data_ptr(), _stream()), "fc_u8_deq")
+            return _new_u8_nhwc(out, m, n, 1, 1, ldy, self._scale, self._zp, two_d=True), f32
         if getattr(self, "_w_scales_dev", None) is not None:
             check(L.i8ie_fc_u8_pc(buf.data_ptr(), ldx, self._w_packed.data_ptr(), self._ldw, self._n_pad,
                                   out.data_ptr(), ldy, m, n, k, oc.data_ptr(), bf.data_ptr(), x.scale(),
@@ -1153,38 +1174,98 @@ class Conv2d(_BaseLayer):
 
 # ---- CUDA-graph replay of a whole quantised forward (used by api.Module.__call__) ------------
 
+MAX_DIRECT_GRAPHS = int(os.environ.get("I8IE_DIRECT_GRAPHS", "8"))   # graphs with the input address baked in, per (shape, device, epoch)
+
+
+class _GraphOutStorage:
+    """Storage of a CUDA-graph result. It aliases the graph's static output buffer until that
+    graph is replayed again; the replay first gives a result that is still referenced its own copy
+    (copy-on-overwrite). A result therefore behaves like the fresh tensor the reference returns,
+    while the usual loop `y = model(x).numpy()` — result consumed and dropped before the next
+    call — costs no device copy per step."""
+    __slots__ = ("_t", "views", "_own", "__weakref__")
+
+    def __init__(self, t):
+        self._t, self.views, self._own = t, 0, False
+
+    @property
+    def t(self):
+        return self._t
+
+    def detach(self):
+        if not self._own:
+            self._t = self._t.clone()      # stream-ordered before the replay that overwrites the buffer
+            self._own = True
+
+
 def graphable(x):
     return isinstance(x, TensorF32) and torch.cuda.is_available()
 
 
-def capture_forward(fn, x):
-    """Captures fn(graph-input tensor) into a CUDA graph. The warm-up calls before this have
-    already created every plan / offset table / packed weight, so nothing allocates through the
-    C ABI or synchronises while the stream is capturing. The input is addressed through a device
-    slot (_SlotStorage), so replays read the caller's buffer in place."""
+def _capture(fn, x, st, slot):
+    """Captures fn(x) into a CUDA graph. The warm-up calls before this have already created every
+    plan / offset table / packed weight, so nothing allocates through the C ABI or synchronises
+    while the stream is capturing. slot is None: x's buffer address is baked into the graph
+    (replayed only for inputs at that address); otherwise the input is addressed through the device
+    slot (_SlotStorage) and a replay works on any buffer. All graphs of one model state share a
+    memory pool (they never run concurrently); each keeps its own output buffer alive."""
     from .api import Tensor
     dev = x.buf.device
-    slot = torch.zeros(2, dtype=torch.int64, device=dev)   # 16-byte slot; [0] = source address
-    keep = x.buf if x.buf.data_ptr() % 16 == 0 else x.buf.clone()
-    slot[0] = keep.data_ptr()
     torch.cuda.synchronize()
     before = _lib.launch_count()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        out = fn(Tensor(TensorF32(_SlotStorage(slot, x.buf.numel(), dev), x._shape)))
+    with torch.cuda.graph(g, pool=st.get("pool")):
+        src = _Storage(x.buf) if slot is None else _SlotStorage(slot, x.buf.numel(), dev)
+        out = fn(Tensor(TensorF32(src, x._shape)))
         out_buf = out.data.buf
     kernels = _lib.launch_count() - before
     if not isinstance(out.data, TensorF32):
         raise RuntimeError("forward() did not return a dequantised tensor")
-    return {"graph": g, "slot": slot, "out_buf": out_buf, "out_shape": list(out.data._shape),
-            "kernels": int(kernels), "replays": 0}
+    st.setdefault("pool", g.pool())
+    return {"graph": g, "out_buf": out_buf, "out_shape": list(out.data._shape), "kernels": int(kernels),
+            "last_out": None}
 
 
-def replay_forward(st, x):
-    src = x.buf
-    if src.data_ptr() % 16 != 0:
-        src = src.clone()
-    st["slot"][:1].fill_(src.data_ptr())      # stream-ordered: the value travels as a kernel argument
-    st["graph"].replay()
-    st["replays"] += 1
-    return TensorF32(_Storage(st["out_buf"].clone()), st["out_shape"])
+def capture_forward(fn, x):
+    """First capture for an input shape: the graph for this input address (state for run_graphed)."""
+    st = {"direct": {}, "indirect": None, "slot": None, "launched": 0, "pool": None}
+    if x.buf.data_ptr() % 16 == 0:
+        st["direct"][x.buf.data_ptr()] = _capture(fn, x, st, None)
+    else:
+        _indirect_graph(fn, x, st)
+    st["graph"] = True
+    return st
+
+
+def _indirect_graph(fn, x, st):
+    if st["indirect"] is None:
+        st["slot"] = torch.zeros(2, dtype=torch.int64, device=x.buf.device)   # 16-byte slot; [0] = source address
+        keep = x.buf if x.buf.data_ptr() % 16 == 0 else x.buf.clone()
+        st["slot"][0] = keep.data_ptr()
+        st["indirect"] = _capture(fn, TensorF32(_Storage(keep), x._shape), st, st["slot"])
+    return st["indirect"]
+
+
+def replay_forward(st, x, fn):
+    """Runs the captured forward on x. Inputs at an address seen before replay the graph that has
+    that address baked in: one graph launch, nothing else on the stream. A new address gets its own
+    graph (up to MAX_DIRECT_GRAPHS — a serving loop cycles through a few allocator blocks); beyond
+    that, and for buffers that are not 16-byte aligned, the slot graph runs: one tiny fill kernel
+    passes the address (and an unaligned buffer is copied first)."""
+    ptr = x.buf.data_ptr()
+    e = st["direct"].get(ptr)
+    if e is None and ptr % 16 == 0 and len(st["direct"]) < MAX_DIRECT_GRAPHS:
+        e = st["direct"][ptr] = _capture(fn, x, st, None)   # (the caller's buffer is not kept alive: a graph only
+        #                                                      replays for a live tensor at exactly this address)
+    if e is None:
+        e = _indirect_graph(fn, x, st)
+        src = x.buf if ptr % 16 == 0 else x.buf.clone()
+        st["slot"][:1].fill_(src.data_ptr())      # stream-ordered: the value travels as a kernel argument
+    prev = e["last_out"]() if e["last_out"] is not None else None
+    if prev is not None:
+        prev.detach()                              # a live result of this graph keeps its values
+    e["graph"].replay()
+    st["launched"] += e["kernels"]
+    stor = _GraphOutStorage(e["out_buf"])
+    e["last_out"] = weakref.ref(stor)
+    return TensorF32(stor, e["out_shape"])

@@ -358,6 +358,10 @@ struct EpiParams {
   // reference's single per-tensor scale (layer.cc:18-19).
   const float* sb_vec = nullptr;
   float sb_min = 0.f, sb_max = 0.f;
+  // fc + dequantize in one launch (i8ie_fc_u8_deq): dense [m, n] fp32 = dequantize(y), i.e.
+  // ((float)y - zp_out) * sc (quantize_utils.cc:38-42). Honoured by fc_head_kernel; the dispatcher
+  // runs the standalone dequantise after any other kernel.
+  float* deq_out = nullptr;
 };
 
 // requant_fast_ok for an epilogue with either kind of weight scale

@@ -309,7 +309,7 @@ int i8ie_conv2d_f32_u8_indirect(i8ie_conv_plan* plan, const float* const* x_slot
 static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
                  int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
                  const float* sb_vec, float sb_min, float sb_max, float sc,
-                 int zp_out, int flags, int32_t* acc_out, int impl, void* stream) {
+                 int zp_out, int flags, int32_t* acc_out, int impl, void* stream, float* deq_out = nullptr) {
   I8IE_REQUIRE(x && w && y && oc && bias_f, "fc_u8: null argument");
   I8IE_REQUIRE(m > 0 && n > 0 && k > 0 && ldx % 16 == 0 && ldw % 16 == 0 && ldy % 16 == 0 && ldx >= k &&
                    ldw >= ldx && ldy >= n && n_pad >= n,
@@ -322,8 +322,15 @@ static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad,
   const bool eligible = !tc_disabled() && k >= 32;
   I8IE_REQUIRE(!(impl == 2 && !eligible), "fc_u8: shape not eligible for the tcgen05 kernel");
   // shape dispatch: a classifier head (<= 16 outputs) is one warp per row, not a 128-row MMA tile
-  if ((impl == 0 || impl == 3) && fc_head_eligible(n_pad, ldx, ldw, ldy, x, w))
+  if ((impl == 0 || impl == 3) && fc_head_eligible(n_pad, ldx, ldw, ldy, x, w)) {
+    ep.deq_out = deq_out;   // the head kernel writes the dequantised logits itself
     return launch_fc_head(x, ldx, w, ldw, y, ldy, m, n, k, ep, (cudaStream_t)stream);
+  }
+  // every other kernel: u8 result first, then the standalone dequantise (same values, one more launch)
+  auto then_dequantize = [&](int rc) {
+    if (rc != I8IE_OK || deq_out == nullptr) return rc;
+    return i8ie_dequantize_rows_u8_f32(y, deq_out, m, n, ldy, sc, zp_out, stream);
+  };
   I8IE_REQUIRE(impl != 3, "fc_u8: shape not eligible for the head kernel (needs n_pad == ldy == 16)");
   if (impl != 1 && eligible) {
     int bn, splits, kb_per;
@@ -334,13 +341,13 @@ static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad,
     rc = g_fc_maps.get(w, n_pad, ldw, bn, 2, &tmB,
                        [&](CUtensorMap* mp) { return tc_encode_weight_map(mp, w, n_pad, ldw, 128, bn); });
     if (rc != I8IE_OK) return rc;
-    return launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream);
+    return then_dequantize(launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream));
   }
   GemmGeom g;
   g.n = m; g.h = 1; g.w = 1; g.cp = ldx;
   g.kh = 1; g.kw = 1; g.stride = 1; g.pad = 0;
   g.oh = 1; g.ow = 1; g.M = m; g.N = n; g.n_pad = n_pad; g.ldw = ldw; g.out_cp = ldy;
-  return launch_simt_igemm(g, x, w, y, ep, 0, (cudaStream_t)stream);
+  return then_dequantize(launch_simt_igemm(g, x, w, y, ep, 0, (cudaStream_t)stream));
 }
 
 int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
@@ -348,6 +355,16 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
                int zp_out, int flags, int32_t* acc_out, int impl, void* stream) {
   return fc_u8(x, ldx, w, ldw, n_pad, y, ldy, m, n, k, oc, bias_f, sa, sb, nullptr, 0.f, 0.f, sc, zp_out, flags, acc_out,
                impl, stream);
+}
+
+int i8ie_fc_u8_deq(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,
+                   int m, int n, int k, const int32_t* oc, const float* bias_f, float sa, float sb,
+                   const float* sb_vec, float sb_min, float sb_max, float sc, int zp_out, int flags, int impl,
+                   float* deq_out, void* stream) {
+  I8IE_REQUIRE(deq_out != nullptr, "fc_u8_deq: null output");
+  I8IE_REQUIRE(sb_vec == nullptr || (sb_min > 0.f && sb_max >= sb_min), "fc_u8_deq: bad per-channel scales");
+  return fc_u8(x, ldx, w, ldw, n_pad, y, ldy, m, n, k, oc, bias_f, sa, sb_vec ? sb_min : sb, sb_vec, sb_min, sb_max, sc,
+               zp_out, flags, nullptr, impl, stream, deq_out);
 }
 
 int i8ie_fc_u8_pc(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,

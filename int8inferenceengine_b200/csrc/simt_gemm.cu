@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) fc_head_kernel(const uint8_t*
     const float sbn = ep.sb_vec ? __ldg(ep.sb_vec + lane) : ep.sb;
     q = fast ? requant_u8_fast(v, ep.sa, sbn, ep.sc, __frcp_rn(ep.sc), zpf) : requant_u8(v, ep.sa, sbn, ep.sc, zpf);
     if (ep.relu) q = max(q, (uint32_t)ep.zp_out);
+    // Module.__call__'s final dequantize (module.py:22-24 -> quantize_utils.cc:54-58) of a classifier head
+    if (ep.deq_out) ep.deq_out[(size_t)m * n + lane] = dequant_f32((uint8_t)q, ep.zp_out, ep.sc);
   }
   y[(size_t)m * ldy + lane] = (uint8_t)q;
 }

@@ -806,13 +806,18 @@ struct Stem2Params {
   int in_zp;
   int f_stages, f_stage_bytes;   // fp32 row ring: [rows_per_tile][c][w] floats per stage
   int pf_tiles;                  // L2 prefetch distance of the fp32 rows, in tiles (0 = off)
-  // dev-only timeline (I8IE_STEM2_TRACE=<file>): CTA 0 records clock64() at kTraceEvents points of each of
-  // its first kTraceTiles tiles — trace[tile][event]; nullptr in production
+  // dev-only timeline (build with I8IE_NVCC_EXTRA=-DI8IE_STEM_TRACE, run with I8IE_STEM2_TRACE=<file>): CTA 0
+  // records clock64() at kTraceEvents points of each of its first kTraceTiles tiles — trace[tile][event];
+  // compiled out of the production library (the per-tile checks cost 2.4 % of the kernel's instructions)
   long long* trace;
 };
 constexpr int kTraceTiles = 24, kTraceEvents = 16;
 __device__ __forceinline__ void stem_trace(const Stem2Params& sp, uint32_t it, int ev) {
+#ifdef I8IE_STEM_TRACE
   if (sp.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceTiles) sp.trace[it * kTraceEvents + ev] = clock64();
+#else
+  (void)sp; (void)it; (void)ev;
+#endif
 }
 
 // Per-role tile / ring cursors of the stem kernel, advanced incrementally: every role used to divide the
@@ -1848,7 +1853,11 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   sp.pf_tiles = 8;
   if (const char* e = std::getenv("I8IE_STEM2_PF")) sp.pf_tiles = std::atoi(e);
   sp.trace = nullptr;
+#ifdef I8IE_STEM_TRACE
   const char* trace_path = fq ? std::getenv("I8IE_STEM2_TRACE") : nullptr;
+#else
+  const char* trace_path = nullptr;
+#endif
   static long long* d_trace = nullptr;
   if (trace_path != nullptr) {   // dev only: eager launches, synchronises
     if (d_trace == nullptr) I8IE_CUDA_OK(cudaMalloc(&d_trace, sizeof(long long) * kTraceTiles * kTraceEvents));

@@ -110,6 +110,43 @@ def test_linear_vs_oracle(shape, impl):
     assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
 
 
+@pytest.mark.parametrize("shape", [(100, 4096, 10), (5, 784, 10), (1, 64, 16), (7, 300, 24), (130, 512, 300)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_linear_with_fused_dequantize(shape, relu):
+    """i8ie_fc_u8_deq: the last fc + Module.__call__'s dequantize (module.py:22-24) through one entry
+    point — classifier heads (<= 16 outputs) in one kernel, other shapes fc + dequantise. Both the u8
+    result and the fp32 logits against the oracle (fully_connected.cc:22-52, quantize_utils.cc:38-42)."""
+    m, k, n = shape
+    rng = np.random.default_rng(7 * m + k + n)
+    a = np.sqrt(6.0 / k)
+    w = rng.uniform(-a, a, size=(n, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(n,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(m, k), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0518), int(rng.integers(0, 256))
+    out_scale, out_zp = np.float32(0.18), int(rng.integers(60, 190))
+    L = make_layer("fc", w, b, (out_scale, out_zp))
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp = port.linear_u8(q, qw, qb, in_scale, in_zp, ws, out_scale, out_zp)
+    if relu:
+        exp = port.relu_u8(exp, out_zp)
+    exp_f = port.dequantize(exp, out_scale, out_zp)
+    y, f32 = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), relu=relu, deq=True)
+    assert np.array_equal(y.numpy(), exp)
+    assert np.array_equal(f32.cpu().numpy().reshape(m, n), exp_f)
+    # the deferred-launch route Module.__call__ takes: layer call -> [relu] -> dequantize
+    t = L(u8_tensor_from_nchw(q, in_scale, in_zp))
+    if relu:
+        t = B.relu(t)
+    assert t._pending("layer") is not None
+    before = B._lib.launch_count()
+    got = B.dequantize(t)
+    launches = B._lib.launch_count() - before
+    assert np.array_equal(got.numpy(), exp_f)
+    assert np.array_equal(t.numpy(), exp)
+    if n <= 16 and k % 16 == 0:
+        assert launches == 1, "a classifier head and its dequantise are one kernel"
+
+
 def test_fc_bias_float_roundtrip_above_2_24():
     """fully_connected.cc:44 adds the bias in fp32 on the s32 accumulator: bits above 2^24 are
     lost exactly as in the reference. Large K with saturated operands reaches that range."""
