@@ -267,6 +267,18 @@ I8IE_API int i8ie_fc_u8_pc(const uint8_t* x, int ldx, const int8_t* w, int ldw, 
                            const float* sb_vec, float sb_min, float sb_max, float sc, int zp_out, int flags,
                            int32_t* acc_out, int impl, void* stream);
 
+/* Small-batch fully_connected.cc:39-41 is a weight stream from HBM. A tiled box of 128-byte rows that lie
+ * `ldw` bytes apart streams at ~2.3 TB/s on B200; the same bytes stored as contiguous 16 KB blocks stream at
+ * ~6 TB/s (tools/ubench/i8_peak.cu). The owner of an fc weight buffer w [n_pad][ldw] (both multiples of 128)
+ * may therefore attach a second buffer of i8ie_fc_weight_tiled_bytes() bytes (16-byte aligned): attach
+ * fills it with [n_pad/128][ldw/128] blocks of 128 rows x 128 bytes in the kernel's swizzled shared-memory
+ * image and registers the pair; later i8ie_fc_u8* calls with this w read the weights through it when the
+ * tcgen05 kernel runs with a 128- or 256-wide N tile (results identical). detach(w) must be called before
+ * either buffer is freed or rewritten. i8ie_fc_weight_tiled_bytes returns 0 for shapes without a tiled form. */
+I8IE_API int64_t i8ie_fc_weight_tiled_bytes(int n_pad, int ldw);
+I8IE_API int i8ie_fc_weight_tiled_attach(const int8_t* w, int n_pad, int ldw, int8_t* w_tiled, void* stream);
+I8IE_API int i8ie_fc_weight_tiled_detach(const int8_t* w);
+
 /* Linear::forward_prop(Tensor<u8>&&) (fully_connected.cc:22-52) of a model's LAST layer together with
  * Module.__call__'s final dequantize (i8ie/module.py:22-24 -> quantize_utils.cc:54-58 -> :38-42):
  * y as i8ie_fc_u8 / i8ie_fc_u8_pc (sb_vec may be NULL: per-tensor scale sb), and

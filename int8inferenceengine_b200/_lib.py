@@ -23,7 +23,7 @@ SYMBOLS = [
     "i8ie_tc_error_poll", "i8ie_peer_exchange_bytes", "i8ie_peer_alloc", "i8ie_peer_open", "i8ie_peer_close",
     "i8ie_peer_free", "i8ie_top1_pack_push", "i8ie_top1_wait_unpack",
     "i8ie_maxpool_u8_nhwc_padded", "i8ie_conv2d_row_mode_cp", "i8ie_conv2d_plan_set_channel_scales", "i8ie_fc_u8_pc",
-    "i8ie_fc_u8_deq",
+    "i8ie_fc_u8_deq", "i8ie_fc_weight_tiled_bytes", "i8ie_fc_weight_tiled_attach", "i8ie_fc_weight_tiled_detach",
 ]
 
 _lib = None
@@ -78,6 +78,10 @@ def load():
     L.i8ie_conv2d_plan_set_channel_scales.argtypes = [vp, vp, f, f]
     L.i8ie_fc_u8_pc.argtypes = [vp, i, vp, i, i, vp, i, i, i, i, vp, vp, f, vp, f, f, f, i, i, vp, i, vp]
     L.i8ie_fc_u8_deq.argtypes = [vp, i, vp, i, i, vp, i, i, i, i, vp, vp, f, f, vp, f, f, f, i, i, i, vp, vp]
+    L.i8ie_fc_weight_tiled_bytes.argtypes = [i, i]
+    L.i8ie_fc_weight_tiled_bytes.restype = i64
+    L.i8ie_fc_weight_tiled_attach.argtypes = [vp, i, i, vp, vp]
+    L.i8ie_fc_weight_tiled_detach.argtypes = [vp]
     L.i8ie_conv2d_f32_u8.argtypes = [vp, vp, f, i, vp, vp, f, f, i, i, vp, vp]
     L.i8ie_conv2d_f32_u8_indirect.argtypes = [vp, vp, f, i, vp, vp, f, f, i, i, vp, vp]
     L.i8ie_quantize_f32_u8_indirect.argtypes = [vp, vp, i64, f, i, vp]

@@ -950,7 +950,28 @@ class Linear(_BaseLayer):
         self._n_pad = _r16(n)
         wp = torch.zeros(self._n_pad, self._ldw, dtype=torch.int8, device="cuda")
         wp[:n, :k] = self._qw_dev
+        self._drop_tiled()
         self._w_packed = wp
+        # small-batch fc streams its weights from HBM: keep a second copy in contiguous, pre-swizzled
+        # 16 KB blocks next to the K-major one (include/i8ie_sm100.h, i8ie_fc_weight_tiled_attach)
+        L = _lib.load()
+        nbytes = int(L.i8ie_fc_weight_tiled_bytes(self._n_pad, self._ldw))
+        if nbytes > 0 and not os.environ.get("I8IE_NO_FC_TILED"):
+            wt = torch.empty(nbytes, dtype=torch.int8, device="cuda")
+            check(L.i8ie_fc_weight_tiled_attach(wp.data_ptr(), self._n_pad, self._ldw, wt.data_ptr(), _stream()),
+                  "fc_weight_tiled_attach")
+            self._w_tiled = wt
+
+    def _drop_tiled(self):
+        if getattr(self, "_w_tiled", None) is not None and self._w_packed is not None:
+            try:
+                _lib.load().i8ie_fc_weight_tiled_detach(self._w_packed.data_ptr())
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+        self._w_tiled = None
+
+    def __del__(self):
+        self._drop_tiled()
 
     def _forward_f32(self, x):
         # Linear::forward_prop(Tensor<float>&&), fully_connected.cc:5-21: fp32 FMA GEMM

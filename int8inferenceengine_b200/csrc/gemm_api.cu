@@ -43,6 +43,23 @@ class MapCache {
 
 MapCache g_fc_maps;
 
+// fc weight buffers that have a tiled, pre-swizzled copy (i8ie_fc_weight_tiled_attach): the owner of both
+// buffers registers the pair and removes it before freeing either, so a hit is never stale.
+struct TiledWeight {
+  const int8_t* w;
+  const int8_t* wt;
+  int n_pad, ldw;
+};
+std::mutex g_tiled_mu;
+std::vector<TiledWeight> g_tiled;
+
+const int8_t* tiled_copy_of(const int8_t* w, int n_pad, int ldw) {
+  std::lock_guard<std::mutex> lk(g_tiled_mu);
+  for (const auto& e : g_tiled)
+    if (e.w == w && e.n_pad == n_pad && e.ldw == ldw) return e.wt;
+  return nullptr;
+}
+
 bool tc_disabled() {
   static const bool off = std::getenv("I8IE_DISABLE_TC") != nullptr;
   return off;
@@ -341,7 +358,9 @@ static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad,
     rc = g_fc_maps.get(w, n_pad, ldw, bn, 2, &tmB,
                        [&](CUtensorMap* mp) { return tc_encode_weight_map(mp, w, n_pad, ldw, 128, bn); });
     if (rc != I8IE_OK) return rc;
-    return then_dequantize(launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream));
+    static const bool no_tiled = std::getenv("I8IE_NO_FC_TILED") != nullptr;
+    const int8_t* wt = (no_tiled || n_pad % bn != 0) ? nullptr : tiled_copy_of(w, n_pad, ldw);   // whole N tiles only
+    return then_dequantize(launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream, wt, ldw));
   }
   GemmGeom g;
   g.n = m; g.h = 1; g.w = 1; g.cp = ldx;
@@ -355,6 +374,29 @@ int i8ie_fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, u
                int zp_out, int flags, int32_t* acc_out, int impl, void* stream) {
   return fc_u8(x, ldx, w, ldw, n_pad, y, ldy, m, n, k, oc, bias_f, sa, sb, nullptr, 0.f, 0.f, sc, zp_out, flags, acc_out,
                impl, stream);
+}
+
+int64_t i8ie_fc_weight_tiled_bytes(int n_pad, int ldw) {
+  if (n_pad <= 0 || ldw <= 0 || n_pad % 128 != 0 || ldw % 128 != 0) return 0;   // shape has no tiled form
+  return (int64_t)n_pad * ldw;
+}
+
+int i8ie_fc_weight_tiled_attach(const int8_t* w, int n_pad, int ldw, int8_t* w_tiled, void* stream) {
+  I8IE_REQUIRE(w && w_tiled && i8ie_fc_weight_tiled_bytes(n_pad, ldw) > 0, "fc_weight_tiled_attach: bad arguments");
+  int rc = tc_fc_tile_weights(w, n_pad, ldw, w_tiled, (cudaStream_t)stream);
+  if (rc != I8IE_OK) return rc;
+  std::lock_guard<std::mutex> lk(g_tiled_mu);
+  for (auto& e : g_tiled)
+    if (e.w == w) { e = TiledWeight{w, w_tiled, n_pad, ldw}; return I8IE_OK; }
+  g_tiled.push_back(TiledWeight{w, w_tiled, n_pad, ldw});
+  return I8IE_OK;
+}
+
+int i8ie_fc_weight_tiled_detach(const int8_t* w) {
+  std::lock_guard<std::mutex> lk(g_tiled_mu);
+  for (size_t i = 0; i < g_tiled.size(); ++i)
+    if (g_tiled[i].w == w) { g_tiled.erase(g_tiled.begin() + (long)i); break; }
+  return I8IE_OK;
 }
 
 int i8ie_fc_u8_deq(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad, uint8_t* y, int ldy,

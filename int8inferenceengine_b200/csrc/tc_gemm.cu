@@ -70,6 +70,14 @@ struct TcParams {
   int mt;
   // CTA-pair kernel: tiles_mp = ceil(tiles_m / 2) 256-row pair tiles; single-CTA kernel: tiles_mp = tiles_m
   int tiles_mp;
+  // fc weight stream (MODE 0, BN a multiple of 128): copy of the weights stored as [n / 128][k / 128] blocks of
+  // 128 rows x 128 bytes, each block already in the 128-byte-swizzled shared-memory image, so a weight stage is
+  // ONE contiguous 16 KB bulk copy per 128 rows instead of a tiled box of 128-byte rows 'ldw' apart. Measured
+  // (tools/ubench/i8_peak.cu, dram_bulk): contiguous 16 KB chunks stream from DRAM at 6.0 TB/s chip-wide, where
+  // the row-strided boxes of the same weights reached 2.3 TB/s. nullptr = tiled map tmB.
+  const int8_t* w_tiled;
+  int wt_nkb;                 // 128-byte K blocks per row of the tiled copy (= ldw / 128)
+  int dbg;                    // dev-only probes of the cluster fc kernel (I8IE_FC_DBG): 1 = no push, 2 = no fold, 4 = no loads
 };
 
 namespace {
@@ -315,7 +323,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
               else
                 ptx::tma_load_2d_a(dst, &tmA, fb, kcol, m0 + t * BM);
             }
-            ptx::tma_load_2d_a(sb + (uint32_t)(j * kSubB), &tmB, fb, kcol, n0);
+            if (MODE == 0 && BK == 128 && BN % 128 == 0 && p.w_tiled != nullptr) {
+              const int8_t* blk = p.w_tiled + ((size_t)(n0 >> 7) * p.wt_nkb + (size_t)(kcol >> 7)) * (128 * 128);
+#pragma unroll
+              for (int h = 0; h < BN / 128; ++h)
+                ptx::bulk_load_1d_a(sb + (uint32_t)(j * kSubB + h * 128 * 128), blk + (size_t)h * p.wt_nkb * (128 * 128),
+                                    128 * 128, fb);
+            } else {
+              ptx::tma_load_2d_a(sb + (uint32_t)(j * kSubB), &tmB, fb, kcol, n0);
+            }
           }
           if (MODE == 1) { cb += BK; if (cb == p.cblocks * BK) { cb = 0; if (++kx == p.kw) { kx = 0; ++ky; } } }
           kcol += BK;
@@ -452,6 +468,198 @@ __global__ void __launch_bounds__(kThreads, 1) tc_igemm_kernel(const __grid_cons
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
+}
+
+// ---- small-M fc: split-K over a thread-block CLUSTER, partial sums folded through distributed shared memory ----
+// A weight stream with one M tile has only N / 128 output tiles, so K is split over the S = 4 CTAs of ONE cluster
+// (fc1 at batch <= 128: 32 clusters of 4 = 128 SMs pull the 37.7 MB of weights). Each CTA accumulates its K slice of
+// the whole 128 x 128 tile in TMEM; then, instead of a round trip of s32 partials through global memory and a second
+// kernel (fc_splitk_reduce_kernel: 14.7 MB written + read and 4.5 us for fc1), rank c of the cluster OWNS the 32
+// columns [32c, 32c + 32): every epilogue warp stages its 32 x 32 accumulator chunk in local shared memory and one
+// bulk copy (cp.async.bulk.shared::cluster.shared::cta, 4 KB) moves it into the owner's receive buffer, completing
+// on the owner's mbarrier; the owner sums the S partials, requantises and stores its 128 x 32 slice. Integer adds
+// commute, so the result is bit-identical to the unsplit sum. (Per-lane st.shared::cluster stores of the same
+// chunks — 16-byte pieces 128 bytes apart — took 16 us for fc1: the SM-to-SM network wants bulk transfers.)
+//   roles: warp 0 TMA / bulk producer, warp 1 MMA issuer, warps 2-17 chunk push + fold
+//   receive buffer [S sources][128 rows][128 bytes] and the 16 x 4 KB staging area re-use the operand ring (free
+//   once every CTA of the cluster has seen its last MMA complete: cluster barrier); 16-byte units of a row are
+//   XOR-swizzled by (row & 7) so that the staging stores (one row per lane) and the fold (4 threads per row) are
+//   bank-conflict free.
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc_fc_cluster_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int BK = 128, S = BN / 32;
+  constexpr int kSubA = BM * BK, kSubB = BN * BK, kStage = kSubA + kSubB;
+  static_assert(BN == 128 && kEpiWarps == 16, "cluster fc: one 32-column chunk per epilogue warp, one owner rank per chunk");
+  constexpr uint32_t kRecvBytes = S * 128 * 128;
+  TcControl<BN>* ctl = reinterpret_cast<TcControl<BN>*>(smem + (size_t)p.stages * kStage);
+  uint64_t* recv_full = &ctl->tmem_full[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const int tile = (int)blockIdx.x / S;                      // one (M tile, N tile) per cluster
+  const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+  const int kb0 = (int)crank * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);   // this CTA's K blocks (>= 1)
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    ptx::mbar_init(&ctl->tmem_full[0], 1);
+    ptx::mbar_init(recv_full, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_arrive_expect_tx(recv_full, (p.dbg & 1) ? 0u : kRecvBytes);   // S sources x 16 KB will land here
+  }
+  if (warp == 1) ptx::tmem_alloc(&ctl->tmem_slot, tmem_cols<BN>());
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_slot;
+  pdl_wait();
+
+  bool ok = true;
+  if (warp == 0) {
+    const uint32_t smem_a = ptx::smem_u32(smem);
+    const uint32_t full_a = ptx::smem_u32(&ctl->full[0]), empty_a = ptx::smem_u32(&ctl->empty[0]);
+    const uint32_t nstages = (uint32_t)p.stages;
+    uint32_t s = 0, ph = 0;
+    int kcol = kb0 * BK;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      if (!ptx::mbar_wait_a(empty_a + 8u * s, ph ^ 1u)) { tc_fail(1); break; }
+      if (ptx::elect_one_sync()) {
+        const uint32_t fb = full_a + 8u * s;
+        if (p.dbg & 4) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+        } else {
+          ptx::mbar_arrive_expect_tx_a(fb, (uint32_t)kStage);
+          const uint32_t sa = smem_a + s * (uint32_t)kStage, sb = sa + (uint32_t)kSubA;
+          ptx::tma_load_2d_a(sa, &tmA, fb, kcol, m0);
+          if (p.w_tiled != nullptr)   // one contiguous pre-swizzled 16 KB block (see TcParams::w_tiled)
+            ptx::bulk_load_1d_a(sb, p.w_tiled + ((size_t)(n0 >> 7) * p.wt_nkb + (size_t)kb) * (128 * 128), 128 * 128, fb);
+          else
+            ptx::tma_load_2d_a(sb, &tmB, fb, kcol, n0);
+        }
+      }
+      __syncwarp();
+      kcol += BK;
+      if (++s == nstages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::make_idesc_i8(BM, BN);
+    const uint32_t desc_hi = ptx::smem_desc_hi<BK>();
+    const uint32_t full_a = ptx::smem_u32(&ctl->full[0]), empty_a = ptx::smem_u32(&ctl->empty[0]);
+    const uint32_t lo0 = ptx::smem_desc_lo(ptx::smem_u32(smem));
+    const uint32_t nstages = (uint32_t)p.stages;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+    uint32_t s = 0, ph = 0, accf = 0;
+    bool alive = true;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      if (!ptx::mbar_wait_a(full_a + 8u * s, ph)) { tc_fail(2); alive = false; break; }
+      ptx::tc_fence_after();
+      if (ptx::elect_one_sync()) {
+        const uint32_t a_lo = lo0 + s * (uint32_t)(kStage >> 4), b_lo = a_lo + (uint32_t)(kSubA >> 4);
+#pragma unroll
+        for (int k = 0; k < BK / 32; ++k) {
+          ptx::mma_i8_ss_lohi(tbase, a_lo + (uint32_t)((k * 32) >> 4), desc_hi, b_lo + (uint32_t)((k * 32) >> 4), desc_hi,
+                              idesc, accf);
+          accf = 1;
+        }
+        ptx::tc_commit_a(empty_a + 8u * s);
+      }
+      __syncwarp();
+      if (++s == nstages) { s = 0; ph ^= 1u; }
+    }
+    if (alive && ptx::elect_one_sync()) ptx::tc_commit(&ctl->tmem_full[0]);
+    __syncwarp();
+    if (!alive && lane == 0) ptx::mbar_arrive(&ctl->tmem_full[0]);
+  }
+
+  // ---- chunk push: warp (quadrant q, owner c) holds columns [32c, 32c + 32) of TMEM lanes [32q, 32q + 32) ----
+  uint32_t v[32];
+  const int quad = warp & 3, owner = (warp - 2) >> 2;
+  // fold mapping: 4 threads per row, 8 columns each; their per-channel terms are fetched now, long before the fold
+  const int et = threadIdx.x - 64;
+  const int frow = et >> 2, cg = et & 3;
+  const int nb = n0 + (int)crank * 32 + cg * 8;
+  int32_t oc8[8];
+  float bias8[8], sb8[8];
+  if (warp >= 2) {
+    const EpiParams& ep = p.ep;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool real = nb + j < p.N;
+      oc8[j] = real ? __ldg(ep.oc + nb + j) : 0;
+      bias8[j] = (real && ep.bias_f) ? __ldg(ep.bias_f + nb + j) : 0.f;
+      sb8[j] = (real && ep.sb_vec) ? __ldg(ep.sb_vec + nb + j) : ep.sb;
+    }
+    ok = ptx::mbar_wait(&ctl->tmem_full[0], 0);
+    if (!ok) tc_fail(3);
+    ptx::tc_fence_after();
+    ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(owner * 32), v);
+    ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+  }
+  __syncwarp();
+  ptx::cluster_sync_all();   // every CTA's last MMA has completed: every operand ring may now be overwritten
+  if (warp >= 2 && !(p.dbg & 1)) {
+    const uint32_t stage = ptx::smem_u32(smem) + kRecvBytes + (uint32_t)(warp - 2) * 4096u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      ptx::sts128(stage + (uint32_t)lane * 128u + (((uint32_t)u ^ ((uint32_t)lane & 7u)) << 4),
+                  make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the bulk copy's reads
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t dst = ptx::mapa(ptx::smem_u32(smem) + (crank * 128u + (uint32_t)(quad * 32)) * 128u, (uint32_t)owner);
+      ptx::bulk_copy_to_cluster(dst, stage, 4096u, ptx::mapa(ptx::smem_u32(recv_full), (uint32_t)owner));
+    }
+  }
+  if (warp >= 2 && ok && !ptx::mbar_wait(recv_full, 0)) { tc_fail(8); ok = false; }   // the S x 16 KB of partial chunks have landed
+  if (warp >= 2 && !(p.dbg & 2)) {
+    // ---- fold + fused epilogue of this rank's 128 x 32 slice ----
+    const int m = m0 + frow;
+    const uint32_t base = ptx::smem_u32(smem) + (uint32_t)frow * 128u;
+    const uint32_t o0 = ((uint32_t)(2 * cg) ^ ((uint32_t)frow & 7u)) << 4, o1 = ((uint32_t)(2 * cg + 1) ^ ((uint32_t)frow & 7u)) << 4;
+    int32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const uint4 a = ptx::lds128(base + (uint32_t)s * (128u * 128u) + o0);
+      const uint4 b = ptx::lds128(base + (uint32_t)s * (128u * 128u) + o1);
+      acc[0] += (int32_t)a.x; acc[1] += (int32_t)a.y; acc[2] += (int32_t)a.z; acc[3] += (int32_t)a.w;
+      acc[4] += (int32_t)b.x; acc[5] += (int32_t)b.y; acc[6] += (int32_t)b.z; acc[7] += (int32_t)b.w;
+    }
+    if (m < p.M && ok) {
+      const EpiParams& ep = p.ep;
+      const float zpf = (float)ep.zp_out, rcp = __frcp_rn(ep.sc);
+      const uint32_t zlo = ep.relu ? (uint32_t)ep.zp_out : 0u;
+      uint32_t word[2] = {0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = nb + j;
+        uint32_t q = (uint32_t)ep.zp_out;   // pad lanes carry the zero point
+        if (n < p.N) {
+          int32_t a = acc[j] + oc8[j];
+          if (ep.bias_f) a = fc_bias_add(a, bias8[j]);
+          if (ep.acc_out) ep.acc_out[(size_t)m * p.N + n] = a;
+          const uint32_t r = p.fast_requant ? requant_u8_fast(a, ep.sa, sb8[j], ep.sc, rcp, zpf) : requant_u8(a, ep.sa, sb8[j], ep.sc, zpf);
+          q = max(r, zlo);
+        }
+        word[j >> 2] |= q << (8 * (j & 3));
+      }
+      if (nb < p.out_cp) *reinterpret_cast<uint2*>(p.y + (size_t)m * p.out_cp + nb) = make_uint2(word[0], word[1]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols<BN>());
+  __syncwarp();
+  ptx::cluster_sync_all();   // no CTA leaves while a peer's bulk copy may still be reading its staging area
 }
 
 // ---- CTA-pair kernel (cta_group::2): conv with wide N tiles ------------------------------------
@@ -1301,6 +1509,19 @@ __global__ void stem_weight_kernel(const int8_t* __restrict__ wp, int8_t* __rest
 // One thread per (row, 4 channels): a warp reads 512 contiguous bytes of every split (fully
 // coalesced), eight independent 128-bit loads in flight per thread. Integer adds commute, so
 // the reduction order is irrelevant to the result.
+// fc weights [n_pad][ldw] (K-major rows) -> [n_pad / 128][ldw / 128] blocks of 128 rows x 128 bytes in the
+// SWIZZLE_128B shared-memory image: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) * 16).
+__global__ void fc_tile_weight_kernel(const int8_t* __restrict__ w, int8_t* __restrict__ wt, int n_pad, int ldw) {
+  const int nkb = ldw >> 7;
+  const int64_t total = (int64_t)n_pad * (ldw >> 4);   // 16-byte chunks
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / (ldw >> 4)), ch = (int)(i % (ldw >> 4));
+    const int kb = ch >> 3, c = ch & 7, r = row & 127, nt = row >> 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(w + (size_t)row * ldw + (size_t)ch * 16);
+    *reinterpret_cast<uint4*>(wt + ((size_t)nt * nkb + kb) * (128 * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) fc_splitk_reduce_kernel(const int32_t* __restrict__ ws, int splits, int M,
                                                                int N, int ws_ld, int ldy, uint8_t* __restrict__ y,
                                                                const EpiParams ep, int fast) {
@@ -1705,6 +1926,8 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
 // stream): every SM should pull an equal, minimal share of bytes through its ~43 B/clk L2
 // port, so pick the (BN, splits) pair with the fewest bytes per CTA, counting the activation
 // rows each N tile re-reads and the s32 partials it writes and the reduce kernel re-reads.
+bool fc_cluster_ok(int bn, int num_kb, int ldy);
+
 void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_per_out) {
   const int num_kb = (k + 127) / 128;
   const int tiles_m = (m + BM - 1) / BM;
@@ -1727,19 +1950,89 @@ void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_p
       if (best < 0 || cost < best) { best = cost; bn = cand; splits = s; kb_per = per; }
     }
   }
+  // cluster split-K (tc_fc_cluster_kernel: 128-wide N tiles, K over the 4 CTAs of a cluster, partials folded through
+  // distributed shared memory — no scratch round trip, no second kernel) whenever that shape fills most of the chip
+  if (splits > 1 && fc_cluster_ok(128, num_kb, ldy)) {
+    const int ctas = tiles_m * ((ldy + 127) / 128) * 4;
+    if (ctas * 3 >= num_sms() * 2 && ctas <= 2 * num_sms()) { bn = 128; splits = 4; kb_per = (num_kb + 3) / 4; }
+  }
   *bn_out = bn; *splits_out = splits; *kb_per_out = kb_per;
 }
 
+int tc_fc_tile_weights(const int8_t* w, int n_pad, int ldw, int8_t* wt, cudaStream_t stream) {
+  I8IE_REQUIRE(w && wt && n_pad > 0 && n_pad % 128 == 0 && ldw > 0 && ldw % 128 == 0 &&
+                   (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0,
+               "fc weight tiling needs n_pad and ldw to be multiples of 128 and 16-byte aligned buffers (n_pad=%d ldw=%d)", n_pad, ldw);
+  const int64_t total = (int64_t)n_pad * (ldw >> 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  fc_tile_weight_kernel<<<blocks, 256, 0, stream>>>(w, wt, n_pad, ldw);
+  return check_launch("fc_tile_weight_kernel");
+}
+
+// Cluster split-K fc (tc_fc_cluster_kernel): S = bn / 32 CTAs per (M tile, N tile), S <= 8 (portable cluster size).
+// Eligible when every rank gets at least one K block and the output pitch is a multiple of 8.
+template <int BN>
+int launch_fc_cluster_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
+  constexpr int S = BN / 32;
+  constexpr int kStage = BM * 128 + BN * 128;
+  const int ctl_bytes = (int)sizeof(TcControl<BN>);
+  int stages = (227 * 1024 - 1024 - ctl_bytes) / kStage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  I8IE_REQUIRE(stages * kStage >= S * 128 * 128 + kEpiWarps * 4096, "cluster fc: operand ring smaller than receive buffer + staging");
+  p.stages = stages;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.out_cp + BN - 1) / BN;
+  p.splits = S;
+  p.kb_per = (p.num_kb + S - 1) / S;
+  const int smem = stages * kStage + ctl_bytes + 1024;
+  static int attr_smem = 0;
+  auto kern = tc_fc_cluster_kernel<BN>;
+  if (attr_smem < smem) {
+    I8IE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  if (const char* e = std::getenv("I8IE_FC_DBG")) {
+    p.dbg = std::atoi(e);
+    static bool once = false;
+    if (!once) {
+      once = true;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(p.tiles_m * p.tiles_n * S)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = -1;
+      cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+      std::fprintf(stderr, "[i8ie] cluster fc BN=%d S=%d smem=%d stages=%d grid=%d: max active clusters %d\n", BN, S, smem, stages,
+                   p.tiles_m * p.tiles_n * S, nc);
+    }
+  }
+  launch_cluster_pdl(S, kern, dim3((unsigned)(p.tiles_m * p.tiles_n * S)), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
+  return check_launch("tc_fc_cluster_kernel");
+}
+
+bool fc_cluster_ok(int bn, int num_kb, int ldy) {
+  static const bool off = std::getenv("I8IE_NO_FC_CLUSTER") != nullptr;
+  if (off || bn != 128 || ldy % 8 != 0) return false;
+  const int S = bn / 32, per = (num_kb + S - 1) / S;
+  return per * (S - 1) < num_kb;   // the last rank still has a K block
+}
+
 int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
-                 int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream) {
+                 int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream, const int8_t* w_tiled, int ldw) {
   TcParams p{};
   p.M = m; p.N = n; p.out_cp = ldy;
+  if (w_tiled != nullptr && bn % 128 == 0 && ldw % 128 == 0) { p.w_tiled = w_tiled; p.wt_nkb = ldw / 128; }
   p.cblocks = 1; p.ksub = 1; p.num_kb = (k + 127) / 128;
   p.kh = p.kw = 1; p.stride_h = p.stride_w = 1; p.pad = 0; p.H = p.W = p.oh = p.ow = 1;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep);
   if (splits <= 1) return launch_bk<0>(128, bn, tmA, tmB, p, stream);
-  // split K across CTAs, then fold the partial sums (exact: integer adds commute)
+  // split K across the CTAs of a cluster and fold the partial sums through distributed shared memory ...
+  if (fc_cluster_ok(bn, p.num_kb, ldy) && splits == 4) return launch_fc_cluster_bn<128>(tmA, tmB, p, stream);
+  // ... or across independent CTAs, folding through a global scratch buffer (exact either way: integer adds commute)
   p.splits = splits; p.kb_per = kb_per;
   p.ws_ld = ((ldy + bn - 1) / bn) * bn;
   int rc = ensure_workspace(sizeof(int32_t) * (size_t)p.splits * m * p.ws_ld, stream, &p.ws);

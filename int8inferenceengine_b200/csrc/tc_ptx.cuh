@@ -271,6 +271,12 @@ __device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* t
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 1-D bulk copy global -> shared by shared-window addresses (size a multiple of 16 bytes)
+__device__ __forceinline__ void bulk_load_1d_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d_a(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c, int w, int h,
                                                      int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -313,6 +319,28 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 // all threads of all CTAs of the cluster
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared-window address of `saddr` in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t rem;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem) : "r"(saddr), "r"(rank));
+  return rem;
+}
+// bulk copy from this CTA's shared memory into the shared memory of a CTA of the cluster (both addresses and
+// the mbarrier in the shared::cluster window of the DESTINATION); completes on the destination's mbarrier
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void st_cluster128(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (base_lane + t)

@@ -147,6 +147,33 @@ def test_linear_with_fused_dequantize(shape, relu):
         assert launches == 1, "a classifier head and its dequantise are one kernel"
 
 
+@pytest.mark.parametrize("m", [1, 100, 128, 300])
+@pytest.mark.parametrize("nk", [(256, 1152), (384, 4096), (1024, 640)])
+def test_linear_tiled_weight_stream(m, nk):
+    """fc whose weights have the tiled, pre-swizzled copy attached (i8ie_fc_weight_tiled_attach): the tcgen05
+    kernel reads contiguous 16 KB blocks instead of row-strided boxes — with and without split-K, one and
+    several M tiles, 128- and 256-wide N tiles — accumulators and bytes against the oracle."""
+    n, k = nk
+    rng = np.random.default_rng(m + 3 * n + k)
+    a = np.sqrt(6.0 / k)
+    w = rng.uniform(-a, a, size=(n, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(n,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(m, k), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0518), int(rng.integers(0, 256))
+    out_scale, out_zp = np.float32(0.21), int(rng.integers(60, 190))
+    L = make_layer("fc", w, b, (out_scale, out_zp))
+    assert L._w_tiled is not None
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.linear_u8(q, qw, qb, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    acc = torch.empty(m * n, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc), "s32 accumulators differ"
+    assert np.array_equal(out.numpy(), exp)
+    L._drop_tiled()                      # same layer through the tiled tensor map
+    out2 = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=2)
+    assert np.array_equal(out2.numpy(), exp)
+
+
 def test_fc_bias_float_roundtrip_above_2_24():
     """fully_connected.cc:44 adds the bias in fp32 on the s32 accumulator: bits above 2^24 are
     lost exactly as in the reference. Large K with saturated operands reaches that range."""
