@@ -83,6 +83,8 @@ struct i8ie_conv_plan {
   StemGeom stem;
   uint8_t* stem_x;      // bordered superpixel image, rewritten by every call
   int8_t* stem_w;       // [kc_pad][kh][64]
+  int8_t* stem_w48;     // [kc_pad][k48]: K-packed weights of the stem2 kernel (kw <= 12), or nullptr
+  CUtensorMap tmB48;
   CUtensorMap tmA_stem;
   bool stem2;           // smem-resident-row kernel (stride 4, narrow rows)
   // row mode (impl 4): physically padded input, plan-owned [kc_pad][kh][kr] weights
@@ -103,6 +105,7 @@ static void plan_free(i8ie_conv_plan* p) {
   if (p->border_tab) cudaFree(p->border_tab);
   if (p->stem_x) cudaFree(p->stem_x);
   if (p->stem_w) cudaFree(p->stem_w);
+  if (p->stem_w48) cudaFree(p->stem_w48);
   if (p->row_w) cudaFree(p->row_w);
   delete p;
 }
@@ -136,6 +139,7 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
   p->border_tab = nullptr;
   p->stem_x = nullptr;
   p->stem_w = nullptr;
+  p->stem_w48 = nullptr;
   p->row_w = nullptr;
   p->kr = 0;
   p->sb_vec = nullptr;
@@ -201,6 +205,19 @@ i8ie_conv_plan* i8ie_conv2d_plan_create(int n, int c, int h, int w, int cp, int 
       rc = I8IE_ECUDA;
     }
     if (rc == I8IE_OK) rc = tc_encode_weight_map(&p->tmB, p->stem_w, kc_pad, kh * 64, 64, p->bn);
+    const int k48 = p->stem2 ? tc_stem_k48_bytes(g, c) : 0;
+    if (rc == I8IE_OK && k48 > 0) {
+      if (cudaMalloc(&p->stem_w48, (size_t)kc_pad * k48) != cudaSuccess) {
+        set_error("conv2d_plan_create: cudaMalloc of the packed stem weights failed");
+        rc = I8IE_ECUDA;
+      }
+      if (rc == I8IE_OK) rc = tc_stem_pack_weights48(g, c, w_packed, p->stem_w48, 0);
+      if (rc == I8IE_OK && cudaStreamSynchronize(0) != cudaSuccess) {
+        set_error("conv2d_plan_create: stem weight kernel failed");
+        rc = I8IE_ECUDA;
+      }
+      if (rc == I8IE_OK) rc = tc_encode_weight_map(&p->tmB48, p->stem_w48, kc_pad, k48, 32, p->bn);
+    }
     if (rc == I8IE_OK) rc = tc_encode_stem_act_map(&p->tmA_stem, p->stem_x, g, p->stem);
     if (rc != I8IE_OK && impl != 2) {
       // the overlapping-window tensor map was refused: serve the layer with the SIMT kernel
@@ -265,7 +282,8 @@ int i8ie_conv2d_u8(i8ie_conv_plan* plan, const uint8_t* x, uint8_t* y, const int
     int rc = tc_stem_pack_input(plan->g, plan->stem, x, plan->stem_x, zp_in, (cudaStream_t)stream);
     if (rc != I8IE_OK) return rc;
     if (plan->stem2)
-      return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+      return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->stem_w48 ? plan->tmB48 : plan->tmB, plan->bn, y, ep,
+                           (cudaStream_t)stream, plan->stem_w48 != nullptr);
     return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
   }
   if (plan->impl == 4) {   // x = physically padded input (border = zp_in): no border table, exact by construction
@@ -299,13 +317,15 @@ static int conv2d_f32_u8(i8ie_conv_plan* plan, const float* x_nchw, const float*
   if (plan->stem2 && tc_stem2_can_fuse_quantize(plan->g, plan->c, x_nchw, x_slot, in_scale)) {
     // the stem kernel's producer warps quantise the fp32 image straight into its operand ring
     const StemF32Src src{x_nchw, x_slot, in_scale, in_zp};
-    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, &src, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, &src, plan->stem_w48 ? plan->tmB48 : plan->tmB, plan->bn, y, ep,
+                           (cudaStream_t)stream, plan->stem_w48 != nullptr);
   }
   int rc = tc_stem_quantize_input(plan->g, plan->stem, x_nchw, x_slot, plan->stem_x, in_scale, in_zp,
                                   (cudaStream_t)stream);
   if (rc != I8IE_OK) return rc;
   if (plan->stem2)
-    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
+    return launch_tc_stem2(plan->g, plan->stem, plan->stem_x, nullptr, plan->stem_w48 ? plan->tmB48 : plan->tmB, plan->bn, y, ep,
+                           (cudaStream_t)stream, plan->stem_w48 != nullptr);
   return launch_tc_stem(plan->g, plan->tmA_stem, plan->tmB, plan->bn, y, ep, (cudaStream_t)stream);
 }
 

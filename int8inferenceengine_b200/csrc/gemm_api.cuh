@@ -84,8 +84,11 @@ struct StemF32Src {
 };
 bool tc_stem2_can_fuse_quantize(const GemmGeom& g, int c, const float* x, const float* const* xslot, float scale);   // RGB stems
 // f32 == nullptr: rows come from the bordered u8 stem image xs; otherwise the kernel quantises them itself
+// k48: tmB maps the K-packed weights (tc_stem_pack_weights48: 48-byte windows, see Stem2Params::k48_n)
 int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const StemF32Src* f32,
-                    const CUtensorMap& tmB, int bn, uint8_t* y, const EpiParams& ep, cudaStream_t stream);
+                    const CUtensorMap& tmB, int bn, uint8_t* y, const EpiParams& ep, cudaStream_t stream, bool k48 = false);
+int tc_stem_k48_bytes(const GemmGeom& g, int c);
+int tc_stem_pack_weights48(const GemmGeom& g, int c, const int8_t* w_packed, int8_t* ws, cudaStream_t stream);
 int launch_tc_stem(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, uint8_t* y,
                    const EpiParams& ep, cudaStream_t stream);
 

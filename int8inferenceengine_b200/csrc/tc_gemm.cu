@@ -1012,6 +1012,14 @@ struct Stem2Params {
   int c, h, w, pad;
   float in_scale, fast_lim;
   int in_zp;
+  // K packing (kw <= 12): the window of one filter row is 3 superpixels = 48 bytes, so the GEMM K axis is the
+  // concatenation of kh 48-byte windows (kh * 48 bytes, rounded up to 32) instead of kh 64-byte ones: AlexNet conv1
+  // issues 17 MMAs per tile instead of 22. K32 block j covers bytes [32j, 32j + 32) of that axis = two 16-byte
+  // chunks that either lie next to each other in one stem row (LBO = 16) or straddle two filter rows (chunk 0 =
+  // superpixel 2 of row r, chunk 1 = superpixel 0 of row r + 1: LBO = their distance in the operand stage).
+  // k48_a[j] = (chunk-0 offset in the stage >> 4) | (LBO >> 4) << 16, added to the stage's descriptor low word.
+  int k48_n;                     // K32 blocks per tile (0 = 64-byte windows)
+  uint32_t k48_a[24];
   int f_stages, f_stage_bytes;   // fp32 row ring: [rows_per_tile][c][w] floats per stage
   int pf_tiles;                  // L2 prefetch distance of the fp32 rows, in tiles (0 = off)
   // dev-only timeline (build with I8IE_NVCC_EXTRA=-DI8IE_STEM_TRACE, run with I8IE_STEM2_TRACE=<file>): CTA 0
@@ -1051,7 +1059,8 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int w_bytes = sp.kh * BN * 64;          // resident weights, one [BN x 64 B] SW64 tile per filter row
+  // resident weights: one [BN x 64 B] SW64 tile per filter row, or k48_n [BN x 32 B] SW32 tiles (K packing)
+  const int w_bytes = sp.k48_n > 0 ? sp.k48_n * BN * 32 : sp.kh * BN * 64;
   const int a_stage = 4 * sp.nsl * 1024;
   uint8_t* sW = smem;
   uint8_t* sA = smem + w_bytes;
@@ -1105,7 +1114,10 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     // bulk copy each, issued in parallel instead of 15 back-to-back from one thread) =====
     if (lane == 0) {   // weights once
       ptx::mbar_arrive_expect_tx(w_full, (uint32_t)w_bytes);
-      for (int r = 0; r < sp.kh; ++r) ptx::tma_load_2d(sW + (size_t)r * BN * 64, &tmB, w_full, r * 64, 0);
+      if (sp.k48_n > 0)
+        for (int j = 0; j < sp.k48_n; ++j) ptx::tma_load_2d(sW + (size_t)j * BN * 32, &tmB, w_full, j * 32, 0);
+      else
+        for (int r = 0; r < sp.kh; ++r) ptx::tma_load_2d(sW + (size_t)r * BN * 64, &tmB, w_full, r * 64, 0);
     }
     uint32_t it = 0;
     bool alive = true;
@@ -1201,7 +1213,12 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const uint32_t d_tmem = tbase + buf * acc_stride<BN>();
       const uint32_t a_lo0 = (((sa_base + s * (uint32_t)a_stage) & 0x3FFFFu) >> 4) | a_flags;
       const bool leader = ptx::elect_one_sync();
-      if (leader && !(sp.dbg & 2)) {
+      if (leader && !(sp.dbg & 2) && sp.k48_n > 0) {
+        const uint32_t a_base = ((sa_base + s * (uint32_t)a_stage) & 0x3FFFFu) >> 4;
+        const uint32_t b32_hi = ptx::smem_desc_hi<32>();
+        for (int j = 0; j < sp.k48_n; ++j)
+          ptx::mma_i8_ss_lohi(d_tmem, a_base + sp.k48_a[j], a_hi, b_lo0 + (uint32_t)(j * BN * 2), b32_hi, idesc, j != 0 ? 1u : 0u);
+      } else if (leader && !(sp.dbg & 2)) {
         if (KH > 0) {
           constexpr int NSL = (KH + 4 + 3) / 4;
 #pragma unroll
@@ -1504,6 +1521,17 @@ __global__ void stem_weight_kernel(const int8_t* __restrict__ wp, int8_t* __rest
   ws[idx] = (px < kw && ch < c) ? wp[(((size_t)n * kh + r) * kw + px) * cp + ch] : (int8_t)0;
 }
 
+
+// stem weights, K-packed: ws[n][k48], byte 48 * r + 4 * px + ch of the K axis (px < 12), zero beyond kh * 48
+__global__ void stem_weight48_kernel(const int8_t* __restrict__ wp, int8_t* __restrict__ ws, int kc_pad, int c,
+                                     int kh, int kw, int cp, int k48) {
+  const int total = kc_pad * k48;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int b = idx % k48, n = idx / k48;
+  const int r = b / 48, o = b % 48, px = o >> 2, ch = o & 3;
+  ws[idx] = (r < kh && px < kw && ch < c) ? wp[(((size_t)n * kh + r) * kw + px) * cp + ch] : (int8_t)0;
+}
 
 // split-K finish: y[m][n] = requant(sum_s ws[s][m][n] + oc[n] (+ float bias)).
 // One thread per (row, 4 channels): a warp reads 512 contiguous bytes of every split (fully
@@ -2066,6 +2094,21 @@ int tc_stem_pack_weights(const GemmGeom& g, int c, const int8_t* w_packed, int8_
   return check_launch("stem_weight_kernel");
 }
 
+// K packing of the stem2 kernel (see Stem2Params::k48_n): bytes of one packed weight row, 0 = not applicable
+int tc_stem_k48_bytes(const GemmGeom& g, int c) {
+  if (!tc_stem2_eligible(g, c) || g.kw > 12 || std::getenv("I8IE_NO_STEM_K48") != nullptr) return 0;
+  const int n32 = (g.kh * 48 + 31) / 32;
+  return n32 <= 24 ? n32 * 32 : 0;
+}
+
+int tc_stem_pack_weights48(const GemmGeom& g, int c, const int8_t* w_packed, int8_t* ws, cudaStream_t stream) {
+  const int k48 = tc_stem_k48_bytes(g, c);
+  I8IE_REQUIRE(k48 > 0, "stem K packing does not apply to this geometry");
+  const int total = g.n_pad * k48;
+  stem_weight48_kernel<<<(total + 255) / 256, 256, 0, stream>>>(w_packed, ws, g.n_pad, c, g.kh, g.kw, g.cp, k48);
+  return check_launch("stem_weight48_kernel");
+}
+
 int tc_stem_pack_input(const GemmGeom& g, const StemGeom& s, const uint8_t* x, uint8_t* xs, int zp,
                        cudaStream_t stream) {
   const int64_t total = (int64_t)g.n * s.hp * s.wsp;
@@ -2130,11 +2173,22 @@ bool tc_stem2_eligible(const GemmGeom& g, int c) {
 
 template <int BN>
 int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const StemF32Src* f32,
-                    const CUtensorMap& tmB, TcParams p, cudaStream_t stream) {
+                    const CUtensorMap& tmB, TcParams p, cudaStream_t stream, bool k48) {
   Stem2Params sp{};
   sp.n_img = g.n; sp.oh = g.oh; sp.ow = g.ow; sp.kh = g.kh; sp.hp = s.hp; sp.wsp = s.wsp;
   sp.pairs = (g.oh + 1) / 2;
   sp.nsl = (g.kh + 4 + 3) / 4;
+  if (k48) {
+    sp.k48_n = (g.kh * 48 + 31) / 32;
+    auto rowaddr = [&](int i) { return ((i & 3) * sp.nsl + (i >> 2)) * 1024; };
+    for (int j = 0; j < sp.k48_n; ++j) {
+      const int b = 32 * j, r = b / 48, o = b % 48;
+      int start = rowaddr(r < g.kh ? r : g.kh - 1) + (r < g.kh ? o : 0), lbo = 16;
+      if (r < g.kh && o == 32 && r + 1 < g.kh) lbo = rowaddr(r + 1) - rowaddr(r) - 32;   // straddles two filter rows
+      I8IE_REQUIRE(lbo > 0 && lbo % 16 == 0 && (lbo >> 4) < (1 << 14), "stem2 K packing: unsupported row distance %d", lbo);
+      sp.k48_a[j] = (uint32_t)(start >> 4) | ((uint32_t)(lbo >> 4) << 16);
+    }
+  }
   sp.xs = xs;
   const bool fq = f32 != nullptr;
   if (fq) {
@@ -2158,7 +2212,7 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
     sp.trace = d_trace;
   }
 
-  const int w_bytes = g.kh * BN * 64;
+  const int w_bytes = k48 ? sp.k48_n * BN * 32 : g.kh * BN * 64;
   const int a_stage = 4 * sp.nsl * 1024;
   const int ctl_bytes = (int)sizeof(TcControl<BN>);
   const int budget = 227 * 1024 - 1024 - ctl_bytes - w_bytes;
@@ -2223,17 +2277,17 @@ bool tc_stem2_can_fuse_quantize(const GemmGeom& g, int c, const float* x, const 
 }
 
 int launch_tc_stem2(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, const StemF32Src* f32,
-                    const CUtensorMap& tmB, int bn, uint8_t* y, const EpiParams& ep, cudaStream_t stream) {
+                    const CUtensorMap& tmB, int bn, uint8_t* y, const EpiParams& ep, cudaStream_t stream, bool k48) {
   TcParams p{};
   p.M = g.M; p.N = g.N; p.out_cp = g.out_cp;
   p.zp_in = 0; p.border_tab = nullptr; p.y = y; p.ep = ep;
   p.fast_requant = requant_fast_ok(ep);
   I8IE_REQUIRE(bn % 32 == 0 || bn >= g.out_cp, "stem2: N tile %d narrower than the output pitch must be a multiple of 32", bn);
   switch (bn) {
-    case 32:  return launch_stem2_bn<32>(g, s, xs, f32, tmB, p, stream);
-    case 64:  return launch_stem2_bn<64>(g, s, xs, f32, tmB, p, stream);
-    case 96:  return launch_stem2_bn<96>(g, s, xs, f32, tmB, p, stream);
-    case 128: return launch_stem2_bn<128>(g, s, xs, f32, tmB, p, stream);
+    case 32:  return launch_stem2_bn<32>(g, s, xs, f32, tmB, p, stream, k48);
+    case 64:  return launch_stem2_bn<64>(g, s, xs, f32, tmB, p, stream, k48);
+    case 96:  return launch_stem2_bn<96>(g, s, xs, f32, tmB, p, stream, k48);
+    case 128: return launch_stem2_bn<128>(g, s, xs, f32, tmB, p, stream, k48);
   }
   set_error("stem2: unsupported BN %d", bn);
   return I8IE_EINVAL;
@@ -2262,6 +2316,7 @@ int tc_error_sink_init() {
   int* d = nullptr;
   I8IE_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0));
   I8IE_CUDA_OK(cudaMemcpyToSymbol(g_tc_error_host, &d, sizeof(d)));
+
   g_sink_dev[dev] = d;
   g_sink_host[dev] = h;
   return I8IE_OK;

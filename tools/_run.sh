@@ -1,5 +1,3 @@
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s2o_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/s2o_tests.log
-python tools/layer_bench.py --layers fc1,fc2 2>&1 | tail -3
-python tools/step_trace.py --batch 100 --steps 10 > gpurun_out/s2o_step_trace.txt 2>&1
-bash tools/gpu_ab.sh s2o "I8IE_X=1"
+for ns in 0 20 50 100 200; do echo "sleep $ns: $(I8IE_WAIT_SLEEP_NS=$ns python tools/stem_bench.py 2>&1 | tail -1)"; done
+bash tools/gpu_ab.sh s2q "I8IE_WAIT_SLEEP_NS=0" "I8IE_WAIT_SLEEP_NS=50"
