@@ -1980,9 +1980,13 @@ void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_p
   }
   // cluster split-K (tc_fc_cluster_kernel: 128-wide N tiles, K over the 4 CTAs of a cluster, partials folded through
   // distributed shared memory — no scratch round trip, no second kernel) whenever that shape fills most of the chip
-  if (splits > 1 && fc_cluster_ok(128, num_kb, ldy)) {
-    const int ctas = tiles_m * ((ldy + 127) / 128) * 4;
-    if (ctas * 3 >= num_sms() * 2 && ctas <= 2 * num_sms()) { bn = 128; splits = 4; kb_per = (num_kb + 3) / 4; }
+  // Measured (fc1 / fc2 of AlexNet, us): batch 16 11.4 / 12.0 vs 10.1 / 9.8 for independent CTAs + reduce kernel (the
+  // partials are tiny there), batch 64 11.6 / 9.8 vs 12.3 / 9.3, batch 100 11.7 / 9.9 vs 14.7 / 10.7, batch 128
+  // 11.7 / 9.9 vs 17.2 / 12.0; with two M tiles (batch 250) every cluster wave streams the weights again:
+  // 23.0 / 19.5 vs 20.8 / 17.9 — so: exactly one M tile of at least 64 rows.
+  if (splits > 1 && tiles_m == 1 && m >= 64 && fc_cluster_ok(128, num_kb, ldy)) {
+    const int ctas = ((ldy + 127) / 128) * 4;
+    if (ctas * 3 >= num_sms() * 2 && ctas <= num_sms()) { bn = 128; splits = 4; kb_per = (num_kb + 3) / 4; }
   }
   *bn_out = bn; *splits_out = splits; *kb_per_out = kb_per;
 }

@@ -1,3 +1,5 @@
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
-for ns in 0 20 50 100 200; do echo "sleep $ns: $(I8IE_WAIT_SLEEP_NS=$ns python tools/stem_bench.py 2>&1 | tail -1)"; done
-bash tools/gpu_ab.sh s2q "I8IE_WAIT_SLEEP_NS=0" "I8IE_WAIT_SLEEP_NS=50"
+for b in 16 64 100 125 128 200 250 500; do
+  echo "batch $b cluster: $(python tools/layer_bench.py --batch $b --layers fc1,fc2 2>&1 | grep -E '^fc' | awk '{print $1, $3}' | tr '\n' ' ')"
+  echo "batch $b old    : $(I8IE_NO_FC_CLUSTER=1 python tools/layer_bench.py --batch $b --layers fc1,fc2 2>&1 | grep -E '^fc' | awk '{print $1, $3}' | tr '\n' ' ')"
+done
