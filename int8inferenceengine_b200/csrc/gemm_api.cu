@@ -370,8 +370,8 @@ static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad,
   };
   I8IE_REQUIRE(impl != 3, "fc_u8: shape not eligible for the head kernel (needs n_pad == ldy == 16)");
   if (impl != 1 && eligible) {
-    int bn, splits, kb_per;
-    tc_fc_config(m, ldy, k, &bn, &splits, &kb_per);
+    int bn, splits, kb_per, cluster;
+    tc_fc_config(m, ldy, k, &bn, &splits, &kb_per, &cluster);
     CUtensorMap tmA, tmB;
     int rc = g_fc_maps.get(x, m, k, ldx, 1, &tmA, [&](CUtensorMap* mp) { return tc_encode_act_map_rows(mp, x, m, k, ldx); });
     if (rc != I8IE_OK) return rc;
@@ -380,7 +380,7 @@ static int fc_u8(const uint8_t* x, int ldx, const int8_t* w, int ldw, int n_pad,
     if (rc != I8IE_OK) return rc;
     static const bool no_tiled = std::getenv("I8IE_NO_FC_TILED") != nullptr;
     const int8_t* wt = (no_tiled || n_pad % bn != 0) ? nullptr : tiled_copy_of(w, n_pad, ldw);   // whole N tiles only
-    return then_dequantize(launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream, wt, ldw));
+    return then_dequantize(launch_tc_fc(m, n, k, ldy, tmA, tmB, bn, splits, kb_per, y, ep, (cudaStream_t)stream, wt, ldw, cluster));
   }
   GemmGeom g;
   g.n = m; g.h = 1; g.w = 1; g.cp = ldx;

@@ -49,11 +49,12 @@ int tc_pick_bn_pair(const GemmGeom& g, int bk, int* mt_out);   // cost-model til
 int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, int bk, int bn, int cluster,
                    const int32_t* border_tab, uint8_t* y, const EpiParams& ep, int zp_in, cudaStream_t stream,
                    int pair_mt = 1);
-void tc_fc_config(int m, int ldy, int k, int* bn, int* splits, int* kb_per);
+// cluster = 1: K split over a 4-CTA cluster folded through distributed shared memory (tc_fc_cluster_kernel)
+void tc_fc_config(int m, int ldy, int k, int* bn, int* splits, int* kb_per, int* cluster);
 // w_tiled: optional pre-swizzled 128 x 128-byte block copy of the weights (tc_fc_tile_weights), or nullptr
 int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
                  int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream, const int8_t* w_tiled = nullptr,
-                 int ldw = 0);
+                 int ldw = 0, int cluster = 0);
 int tc_fc_tile_weights(const int8_t* w, int n_pad, int ldw, int8_t* wt, cudaStream_t stream);
 int tc_read_error(int* out, bool reset);
 int tc_error_sink_init();         // host-mapped mirror of the protocol-error flag (call outside stream capture)

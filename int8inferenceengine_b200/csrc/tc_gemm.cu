@@ -1956,11 +1956,11 @@ int launch_tc_conv(const GemmGeom& g, const CUtensorMap& tmA, const CUtensorMap&
 // rows each N tile re-reads and the s32 partials it writes and the reduce kernel re-reads.
 bool fc_cluster_ok(int bn, int num_kb, int ldy);
 
-void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_per_out) {
+void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_per_out, int* cluster_out) {
   const int num_kb = (k + 127) / 128;
   const int tiles_m = (m + BM - 1) / BM;
   int bn = pick_bn(ldy);
-  int splits = 1, kb_per = num_kb;
+  int splits = 1, kb_per = num_kb, cluster = 0;
   const bool allow = std::getenv("I8IE_NO_SPLITK") == nullptr && std::getenv("I8IE_TC_BN") == nullptr;
   if (allow && tiles_m * ((ldy + bn - 1) / bn) * 2 <= num_sms() && num_kb >= 2) {
     long long best = -1;
@@ -1986,8 +1986,9 @@ void tc_fc_config(int m, int ldy, int k, int* bn_out, int* splits_out, int* kb_p
   // 23.0 / 19.5 vs 20.8 / 17.9 — so: exactly one M tile of at least 64 rows.
   if (splits > 1 && tiles_m == 1 && m >= 64 && fc_cluster_ok(128, num_kb, ldy)) {
     const int ctas = ((ldy + 127) / 128) * 4;
-    if (ctas * 3 >= num_sms() * 2 && ctas <= num_sms()) { bn = 128; splits = 4; kb_per = (num_kb + 3) / 4; }
+    if (ctas * 3 >= num_sms() * 2 && ctas <= num_sms()) { bn = 128; splits = 4; kb_per = (num_kb + 3) / 4; cluster = 1; }
   }
+  *cluster_out = cluster;
   *bn_out = bn; *splits_out = splits; *kb_per_out = kb_per;
 }
 
@@ -2053,7 +2054,8 @@ bool fc_cluster_ok(int bn, int num_kb, int ldy) {
 }
 
 int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, int bn, int splits,
-                 int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream, const int8_t* w_tiled, int ldw) {
+                 int kb_per, uint8_t* y, const EpiParams& ep, cudaStream_t stream, const int8_t* w_tiled, int ldw,
+                 int cluster) {
   TcParams p{};
   p.M = m; p.N = n; p.out_cp = ldy;
   if (w_tiled != nullptr && bn % 128 == 0 && ldw % 128 == 0) { p.w_tiled = w_tiled; p.wt_nkb = ldw / 128; }
@@ -2063,7 +2065,7 @@ int launch_tc_fc(int m, int n, int k, int ldy, const CUtensorMap& tmA, const CUt
   p.fast_requant = requant_fast_ok(ep);
   if (splits <= 1) return launch_bk<0>(128, bn, tmA, tmB, p, stream);
   // split K across the CTAs of a cluster and fold the partial sums through distributed shared memory ...
-  if (fc_cluster_ok(bn, p.num_kb, ldy) && splits == 4) return launch_fc_cluster_bn<128>(tmA, tmB, p, stream);
+  if (cluster && fc_cluster_ok(bn, p.num_kb, ldy) && splits == 4) return launch_fc_cluster_bn<128>(tmA, tmB, p, stream);
   // ... or across independent CTAs, folding through a global scratch buffer (exact either way: integer adds commute)
   p.splits = splits; p.kb_per = kb_per;
   p.ws_ld = ((ldy + bn - 1) / bn) * bn;

@@ -174,6 +174,30 @@ def test_linear_tiled_weight_stream(m, nk):
     assert np.array_equal(out2.numpy(), exp)
 
 
+@pytest.mark.parametrize("shape", [(100, 1024, 4096), (64, 520, 3200), (128, 4096, 4096), (97, 2304, 3210)])
+def test_linear_cluster_split_k(shape):
+    """Wide small-batch fc (one M tile of >= 64 rows, enough N tiles to fill the chip): K is split over a 4-CTA
+    cluster and the partial sums are folded through distributed shared memory (tc_fc_cluster_kernel). K tails,
+    N that is not a multiple of the tile, relu, the s32 accumulators and the bytes against the oracle."""
+    m, k, n = shape
+    rng = np.random.default_rng(m + k + n)
+    a = np.sqrt(6.0 / k)
+    w = rng.uniform(-a, a, size=(n, k)).astype(np.float32)
+    b = rng.uniform(-0.05, 0.05, size=(n,)).astype(np.float32)
+    q = rng.integers(0, 256, size=(m, k), dtype=np.uint8)
+    in_scale, in_zp = np.float32(0.0518), int(rng.integers(0, 256))
+    out_scale, out_zp = np.float32(0.25), int(rng.integers(60, 190))
+    L = make_layer("fc", w, b, (out_scale, out_zp))
+    qw, qb, ws = port.quantize_weight(w, b)
+    exp, exp_acc = port.linear_u8(q, qw, qb, in_scale, in_zp, ws, out_scale, out_zp, want_acc=True)
+    acc = torch.empty(m * n, dtype=torch.int32, device="cuda")
+    out = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), acc_out=acc, impl=2)
+    assert np.array_equal(acc.cpu().numpy().reshape(m, n), exp_acc), "s32 accumulators differ"
+    assert np.array_equal(out.numpy(), exp)
+    out_r = L._forward_u8(u8_tensor_from_nchw(q, in_scale, in_zp), impl=2, relu=True)
+    assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
+
+
 def test_fc_bias_float_roundtrip_above_2_24():
     """fully_connected.cc:44 adds the bias in fp32 on the s32 accumulator: bits above 2^24 are
     lost exactly as in the reference. Large K with saturated operands reaches that range."""
