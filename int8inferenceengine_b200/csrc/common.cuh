@@ -66,9 +66,25 @@ inline int num_sms() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-inline int pdl_enabled() {   // measured on B200: no gain for this chain (kernels are drain/fill bound), so opt-in
-  static const int on = std::getenv("I8IE_PDL") != nullptr ? 1 : 0;
-  return on;
+// Kernel families for the per-family PDL switch (I8IE_PDL_MASK = sum of the bits; I8IE_PDL=1 = all).
+// A launch site tags itself with PdlFamily f(kPdl...) before calling launch_pdl / launch_cluster_pdl.
+enum : int { kPdlStem = 1, kPdlPairConv = 2, kPdlPool = 4, kPdlFcCluster = 8, kPdlFcHead = 16, kPdlOther = 32, kPdlTc = 64 };
+inline int& pdl_family_slot() {
+  static thread_local int f = kPdlOther;
+  return f;
+}
+struct PdlFamily {
+  int saved;
+  explicit PdlFamily(int f) : saved(pdl_family_slot()) { pdl_family_slot() = f; }
+  ~PdlFamily() { pdl_family_slot() = saved; }
+};
+inline int pdl_enabled() {   // measured on B200 (profiles/r02_stem_probes.md): which families gain, which lose
+  // default: the tensor-core GEMM kernels and the classifier head (step 0.1931 -> 0.1828 ms at batch 100); pools lose
+  // 3 us when they become resident early next to a conv CTA, the stem gains nothing (its predecessor is tiny)
+  static const int mask = std::getenv("I8IE_PDL") != nullptr ? 0x7fffffff
+                          : (std::getenv("I8IE_PDL_MASK") != nullptr ? std::atoi(std::getenv("I8IE_PDL_MASK"))
+                                                                     : (kPdlPairConv | kPdlFcCluster | kPdlFcHead | kPdlTc));
+  return (mask & pdl_family_slot()) != 0 ? 1 : 0;
 }
 
 template <typename... KArgs, typename... Args>

@@ -854,6 +854,7 @@ int i8ie_maxpool_u8_nhwc(const uint8_t* x, uint8_t* y, int n, int h, int w, int 
   cudaStream_t s = (cudaStream_t)stream;
 #define I8IE_POOL_KS(KERNEL, GRID, SMEM, ...)                                                     \
   do {                                                                                            \
+    PdlFamily fam_(kPdlPool);                                                                      \
     if (ksize == 3) launch_pdl(KERNEL<3>, dim3(GRID), dim3(kThreads), SMEM, s, __VA_ARGS__);       \
     else if (ksize == 2) launch_pdl(KERNEL<2>, dim3(GRID), dim3(kThreads), SMEM, s, __VA_ARGS__);  \
     else launch_pdl(KERNEL<0>, dim3(GRID), dim3(kThreads), SMEM, s, __VA_ARGS__);                  \
@@ -886,6 +887,7 @@ int i8ie_maxpool_u8_nhwc_padded(const uint8_t* x, uint8_t* y, int n, int h, int 
   I8IE_REQUIRE(rows < (1ll << 30), "maxpool_padded: too many rows");
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t zp4 = (uint32_t)pad_value * 0x01010101u;
+  PdlFamily fam_(kPdlPool);
   if (ksize == 3)
     launch_pdl(maxpool_nhwc_rows_padded_kernel<3>, dim3((unsigned)rows), dim3(kThreads), 0, s, x, y, h, w, c, cp, ksize,
                stride, oh, ow, out_cp, out_pad, zp4);

@@ -211,6 +211,7 @@ bool fc_head_eligible(int n_pad, int ldx, int ldw, int ldy, const void* x, const
 int launch_fc_head(const uint8_t* x, int ldx, const int8_t* w, int ldw, uint8_t* y, int ldy, int m, int n, int k,
                    const EpiParams& ep, cudaStream_t stream) {
   const int kvec = (k + 15) / 16;   // the [k, ldx) tail multiplies zero weight lanes
+  PdlFamily fam_(kPdlFcHead);
   launch_pdl(fc_head_kernel, dim3(m), dim3(kHeadWarps * 32), 0, stream, x, ldx, w, ldw, y, ldy, n, kvec, ep,
              requant_fast_ok(ep) ? 1 : 0);
   return check_launch("fc_head_kernel");

@@ -521,6 +521,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fc_cluster_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
+  // The weights do not depend on the previous kernel: with programmatic dependent launch this CTA may be resident
+  // while its predecessor still runs, so the producer asks for the weight halves of the first ring pass BEFORE
+  // griddepcontrol.wait and adds the activation tiles (the predecessor's output) after it.
+  const int npre = min(p.stages, kb1 - kb0);
+  auto load_w = [&](uint32_t sb, uint32_t fb, int kb, int kcol) {
+    if (p.w_tiled != nullptr)   // one contiguous pre-swizzled 16 KB block (see TcParams::w_tiled)
+      ptx::bulk_load_1d_a(sb, p.w_tiled + ((size_t)(n0 >> 7) * p.wt_nkb + (size_t)kb) * (128 * 128), 128 * 128, fb);
+    else
+      ptx::tma_load_2d_a(sb, &tmB, fb, kcol, n0);
+  };
+  if (warp == 0 && !(p.dbg & 4)) {
+    if (ptx::elect_one_sync()) {
+      for (int i = 0; i < npre; ++i) {
+        const uint32_t fb = ptx::smem_u32(&ctl->full[i]);
+        ptx::mbar_arrive_expect_tx_a(fb, (uint32_t)kStage);
+        load_w(ptx::smem_u32(smem) + (uint32_t)i * (uint32_t)kStage + (uint32_t)kSubA, fb, kb0 + i, (kb0 + i) * BK);
+      }
+    }
+    __syncwarp();
+  }
   pdl_wait();
 
   bool ok = true;
@@ -531,19 +551,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fc_cluster_kernel(const __grid
     uint32_t s = 0, ph = 0;
     int kcol = kb0 * BK;
     for (int kb = kb0; kb < kb1; ++kb) {
-      if (!ptx::mbar_wait_a(empty_a + 8u * s, ph ^ 1u)) { tc_fail(1); break; }
+      const bool first_pass = kb - kb0 < npre;   // stage untouched so far, its weight half is already on the way
+      if (!first_pass && !ptx::mbar_wait_a(empty_a + 8u * s, ph ^ 1u)) { tc_fail(1); break; }
       if (ptx::elect_one_sync()) {
         const uint32_t fb = full_a + 8u * s;
         if (p.dbg & 4) {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
         } else {
-          ptx::mbar_arrive_expect_tx_a(fb, (uint32_t)kStage);
           const uint32_t sa = smem_a + s * (uint32_t)kStage, sb = sa + (uint32_t)kSubA;
+          if (!first_pass) {
+            ptx::mbar_arrive_expect_tx_a(fb, (uint32_t)kStage);
+            load_w(sb, fb, kb, kcol);
+          }
           ptx::tma_load_2d_a(sa, &tmA, fb, kcol, m0);
-          if (p.w_tiled != nullptr)   // one contiguous pre-swizzled 16 KB block (see TcParams::w_tiled)
-            ptx::bulk_load_1d_a(sb, p.w_tiled + ((size_t)(n0 >> 7) * p.wt_nkb + (size_t)kb) * (128 * 128), 128 * 128, fb);
-          else
-            ptx::tma_load_2d_a(sb, &tmB, fb, kcol, n0);
         }
       }
       __syncwarp();
@@ -1684,6 +1704,7 @@ int launch_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  PdlFamily fam_(kPdlTc);
   launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm_kernel");
 }
@@ -1771,6 +1792,7 @@ int launch_pair_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams p, c
   const int tiles = p.tiles_mp * p.tiles_n;
   const int max_clusters = num_sms() / 2;
   const int grid = (tiles < max_clusters ? tiles : max_clusters) * 2;
+  PdlFamily fam_(kPdlPairConv);
   launch_cluster_pdl(2, kern, dim3(grid), dim3(kThreads2), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_igemm2_kernel");
 }
@@ -2042,6 +2064,7 @@ int launch_fc_cluster_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParam
                    p.tiles_m * p.tiles_n * S, nc);
     }
   }
+  PdlFamily fam_(kPdlFcCluster);
   launch_cluster_pdl(S, kern, dim3((unsigned)(p.tiles_m * p.tiles_n * S)), dim3(kThreads), (size_t)smem, stream, tmA, tmB, p);
   return check_launch("tc_fc_cluster_kernel");
 }
@@ -2251,6 +2274,7 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   const int tiles = sp.n_img * sp.pairs;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const int threads = fq ? stem_threads<BN, true>() : stem_threads<BN, false>();
+  PdlFamily fam_(kPdlStem);
   launch_pdl(kern, dim3(grid), dim3(threads), (size_t)smem, stream, tmB, p, sp);
   if (trace_path != nullptr) {
     std::vector<long long> h(kTraceTiles * kTraceEvents);
