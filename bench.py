@@ -80,6 +80,9 @@ def peaks():
 # ------------------------------------------------------------------------------------------
 # clocks: poll NVML during the timed region
 # ------------------------------------------------------------------------------------------
+SAMPLE_PERIOD_S = float(os.environ.get("I8IE_BENCH_SAMPLE_MS", "10")) * 1e-3
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -117,7 +120,7 @@ class ClockSampler(threading.Thread):
                 pass
             # 10 ms: ~50 samples over the 0.5 s loaded window; a faster poll only competes with the launch
             # loop for the GIL and, at N ranks, N pollers queue on the driver's NVML lock
-            time.sleep(0.010)
+            time.sleep(SAMPLE_PERIOD_S)
 
     def stop(self):
         self._stop_evt.set()
@@ -431,15 +434,18 @@ def run_ours(args):
     if world == 1:
         for i in range(ring + 3):
             step(i)
+    # the NVML poller is created and started BEFORE the warm-up (nvmlInit takes a rank-dependent number of
+    # milliseconds: done after the barrier it made the ranks enter the timed loop that far apart, and with a
+    # lock-step exchange in every step the early ranks' 50-step window absorbed the whole skew)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(max(args.warmup, 3)):
         step(i)
     sync_all()
     stage("warm-up done")
 
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _lib.launch_count() + model.graph_launches() + (sharded.launches() if sharded else 0)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active = True
     if args.profiler_range:      # ncu --profile-from-start off: capture exactly the timed steps
         torch.cuda.profiler.start()

@@ -68,7 +68,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Kernel families for the per-family PDL switch (I8IE_PDL_MASK = sum of the bits; I8IE_PDL=1 = all).
 // A launch site tags itself with PdlFamily f(kPdl...) before calling launch_pdl / launch_cluster_pdl.
-enum : int { kPdlStem = 1, kPdlPairConv = 2, kPdlPool = 4, kPdlFcCluster = 8, kPdlFcHead = 16, kPdlOther = 32, kPdlTc = 64 };
+enum : int { kPdlStem = 1, kPdlPairConv = 2, kPdlPool = 4, kPdlFcCluster = 8, kPdlFcHead = 16, kPdlOther = 32, kPdlTc = 64,
+       kPdlExchange = 128 };
 inline int& pdl_family_slot() {
   static thread_local int f = kPdlOther;
   return f;
@@ -83,7 +84,7 @@ inline int pdl_enabled() {   // measured on B200 (profiles/r02_stem_probes.md): 
   // 3 us when they become resident early next to a conv CTA, the stem gains nothing (its predecessor is tiny)
   static const int mask = std::getenv("I8IE_PDL") != nullptr ? 0x7fffffff
                           : (std::getenv("I8IE_PDL_MASK") != nullptr ? std::atoi(std::getenv("I8IE_PDL_MASK"))
-                                                                     : (kPdlPairConv | kPdlFcCluster | kPdlFcHead | kPdlTc));
+                                                                     : (kPdlPairConv | kPdlFcCluster | kPdlFcHead | kPdlTc | kPdlExchange));
   return (mask & pdl_family_slot()) != 0 ? 1 : 0;
 }
 

@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(1024) top1_pack_push_kernel(const float* __res
                                                               int cols, PeerTable peers, int world, int rank,
                                                               long long chunk_bytes, unsigned long long* seq_counter) {
   __shared__ int s_cnt[32];
+  pdl_launch_dependents();
+  pdl_wait();   // resident while the classifier head still runs; its logits are read from here on
   const unsigned long long seq = *seq_counter + 1ull;
   int cnt = 0;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(1024) top1_wait_unpack_kernel(const uint8_t* _
                                                                 float* __restrict__ logits_all,
                                                                 long long* __restrict__ agree_total, int* __restrict__ err) {
   __shared__ int s_bad;
+  pdl_launch_dependents();
+  pdl_wait();   // resident while the pack kernel runs; it has completed (and bumped seq) from here on
   const unsigned long long seq = *seq_counter;   // the pack kernel of this step ran before us on this stream
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
@@ -195,9 +199,10 @@ int i8ie_top1_pack_push(const float* logits, const int64_t* ref_argmax, int rows
     I8IE_REQUIRE(peer_bases[p] != nullptr, "top1_pack_push: peer %d is not mapped", p);
     t.base[p] = reinterpret_cast<uint8_t*>(peer_bases[p]);
   }
-  top1_pack_push_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(ref_argmax), rows,
-                                                              cols, t, world, rank, (long long)chunk_bytes,
-                                                              reinterpret_cast<unsigned long long*>(seq_counter));
+  PdlFamily fam_(kPdlExchange);
+  launch_pdl(top1_pack_push_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, logits,
+             reinterpret_cast<const long long*>(ref_argmax), rows, cols, t, world, rank, (long long)chunk_bytes,
+             reinterpret_cast<unsigned long long*>(seq_counter));
   return check_launch("top1_pack_push_kernel");
 }
 
@@ -205,10 +210,11 @@ int i8ie_top1_wait_unpack(const void* mine, int world, int64_t chunk_bytes, cons
                           int64_t* agree_total, void* stream) {
   I8IE_REQUIRE(mine && seq_counter && logits_all && agree_total && world >= 1 && world <= kMaxWorld && chunk_bytes > 0,
                "top1_wait_unpack: bad arguments");
-  top1_wait_unpack_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint8_t*>(mine), world, (long long)chunk_bytes,
-      reinterpret_cast<const unsigned long long*>(seq_counter), logits_all, reinterpret_cast<long long*>(agree_total),
-      tc_error_sink_device_ptr());
+  PdlFamily fam_(kPdlExchange);
+  launch_pdl(top1_wait_unpack_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream,
+             reinterpret_cast<const uint8_t*>(mine), world, (long long)chunk_bytes,
+             reinterpret_cast<const unsigned long long*>(seq_counter), logits_all, reinterpret_cast<long long*>(agree_total),
+             tc_error_sink_device_ptr());
   return check_launch("top1_wait_unpack_kernel");
 }
 
