@@ -514,9 +514,22 @@ class _DeferredLayer:
     def with_relu(self):
         return _DeferredLayer(self.layer, self.x, True)
 
-    def launch(self):
-        y = self.layer._forward_u8(self.x, relu=self.relu or self.layer.fuse_relu)
+    def launch(self, out_cp=None):
+        kw = {"out_cp": out_cp} if out_cp is not None else {}
+        y = self.layer._forward_u8(self.x, relu=self.relu or self.layer.fuse_relu, **kw)
         return y._st, y._layout, y._geom
+
+
+def _launch_conv_narrow(x):
+    """x is about to be read by a max-pool that chooses its own OUTPUT pitch (padded layout of a row-mode
+    convolution, or the dense NCHW order of a flatten). If x is a convolution that has not been launched yet,
+    let it store its real channels only (pitch round_up(C, 16)) instead of the K-block-friendly pitch a following
+    convolution would want: AlexNet conv1 writes 96 instead of 128 bytes per pixel, and pool1 reads as much."""
+    pend = x._pending("layer")
+    if pend is not None and isinstance(pend.layer, Conv2d) and len(x._shape) == 4:
+        c = x._shape[1]
+        if _r16(c) < _act_pitch(c) and not os.environ.get("I8IE_NO_NARROW_PITCH"):
+            x._resolve(*pend.launch(out_cp=_r16(c)))
 
 
 class _DeferredPool:
@@ -533,6 +546,8 @@ class _DeferredPool:
         x, k, s = self.x, self.k, self.s
         n, c, h, w = x._shape
         oh, ow = (h - k) // s + 1, (w - k) // s + 1
+        if self.out_nchw:
+            _launch_conv_narrow(x)
         buf, cp = x._as_nhwc(n, c, h, w)
         out = _u8_empty(n * oh * ow * (c if self.out_nchw else cp), buf.device)
         check(L.i8ie_maxpool_u8_nhwc(buf.data_ptr(), out.data_ptr(), n, h, w, c, cp, k, s,
@@ -548,6 +563,7 @@ class _DeferredPool:
         x, k, s = self.x, self.k, self.s
         n, c, h, w = x._shape
         oh, ow = (h - k) // s + 1, (w - k) // s + 1
+        _launch_conv_narrow(x)
         buf, cp = x._as_nhwc(n, c, h, w)
         out = torch.empty(n * (oh + 2 * out_pad) * (ow + 2 * out_pad) * out_cp + 128, dtype=torch.uint8,
                           device=buf.device)
@@ -707,32 +723,84 @@ def max_pool2d(x, kernel_size, strides):
 
 class Calibrator:
     """Activation-range collector. The reference keeps a 1000-slot sample with random
-    replacement from an unseeded mt19937 (calibrator.cc:6-23) and takes min/max of the sorted
-    slots (get_range(1), :24-37). Here the range is the true min/max of everything seen —
-    a warp-shuffle/block reduction on the device (i8ie_minmax_f32) — which is what the
-    reference computes whenever <=1000 values were seen; for exactly that regime the first
-    1000 values are also kept so the zero-filled-tail quirk is reproduced."""
+    replacement from a random_device-seeded mt19937 (calibrator.cc:6-23) and takes min/max of the
+    sorted slots (get_range(1), :24-37).
 
-    def __init__(self):
+    mode "minmax" (default): the range is the true min/max of everything seen — a warp-shuffle /
+    block reduction on the device (i8ie_minmax_f32), deterministic — which is what the reference
+    computes whenever <=1000 values were seen; for exactly that regime the first 1000 values are
+    also kept so the zero-filled-tail quirk is reproduced. Beyond 1000 values the
+    reference's sample is ~1000 of the LAST few thousand values in memory order (each later value
+    overwrites a uniformly chosen slot with probability 1000/2001), so its ranges are narrower and
+    differ from run to run; this mode's scales are systematically wider than that.
+
+    mode "reference" (opt-in: `Calibrator.default_mode = "reference"` or I8IE_CALIBRATOR=reference):
+    a seeded emulation of that sampling process, exact in distribution per slot — the element a slot
+    holds at the end is the last one that hit it, i.e. `G` positions before the end of the stream
+    with G ~ Geometric(1/2001) — so a model calibrated here gets ranges distributed like the
+    reference's (and reproducible for a fixed `Calibrator.seed`)."""
+
+    default_mode = os.environ.get("I8IE_CALIBRATOR", "minmax")
+    seed = 0
+    _instances = 0
+
+    def __init__(self, mode=None):
+        self.mode = mode or Calibrator.default_mode
+        if self.mode not in ("minmax", "reference"):
+            raise ValueError(f"unknown calibrator mode {self.mode!r}")
         self.out_cnt = 0
         self.head = []          # first <=1000 samples, host copies
         self.mn = None
         self.mx = None
         self._ws = None
         self._out = None
+        self.slots = None       # "reference" mode: the 1000-slot sample (host)
+        self._rng = np.random.default_rng([Calibrator.seed, Calibrator._instances])
+        Calibrator._instances += 1
 
     def new_range(self, device):
         """Device {min, max} pair a forward kernel folds its outputs into (fused calibrator pass)."""
         return torch.tensor([np.finfo(np.float32).max, -np.finfo(np.float32).max], dtype=torch.float32, device=device)
+
+    @staticmethod
+    def replacement_indices(n, first, rng):
+        """calibrator.cc:13-21 for the elements [first, n) of one sample() call, in distribution: for
+        every slot the index of the LAST element that hit it (uniform slot pick out of 2 * 1000 + 1, so
+        a given slot is hit with probability 1/2001 per element), or -1 if none did.
+        Returns int64[1000]."""
+        g = rng.geometric(1.0 / (2 * NUM_SAMPLES + 1), size=NUM_SAMPLES) - 1     # misses counted from the end
+        idx = (n - 1) - g
+        return np.where(idx >= first, idx, -1).astype(np.int64)
+
+    def _sample_slots(self, t, take):
+        """"reference" mode bookkeeping for one sample() call; `take` leading elements went to free slots."""
+        n = t.numel()
+        if self.slots is None:
+            self.slots = np.zeros(NUM_SAMPLES, np.float32)      # value-initialised (layer.cc:33)
+        flat = t.reshape(-1)
+        if take:
+            self.slots[self.out_cnt:self.out_cnt + take] = flat[:take].cpu().numpy()
+        if n > take:
+            idx = self.replacement_indices(n, take, self._rng)
+            hit = np.nonzero(idx >= 0)[0]
+            if hit.size:
+                src = torch.from_numpy(idx[hit]).to(flat.device)
+                self.slots[hit] = flat.index_select(0, src).cpu().numpy()
+
+    def _take(self, t):
+        n = t.numel()
+        take = min(NUM_SAMPLES - self.out_cnt, n) if self.out_cnt < NUM_SAMPLES else 0
+        if self.mode == "reference":
+            self._sample_slots(t, take)
+        elif take:
+            self.head.append(t.reshape(-1)[:take].cpu().numpy())
 
     def sample_range(self, t, mm):
         """sample() for a layer output whose {min, max} the producing kernel already reduced."""
         n = t.numel()
         if n == 0:
             return
-        if self.out_cnt < NUM_SAMPLES:
-            take = min(NUM_SAMPLES - self.out_cnt, n)
-            self.head.append(t.reshape(-1)[:take].cpu().numpy())
+        self._take(t)
         mn, mx = (float(v) for v in mm.cpu().numpy())
         self.mn = mn if self.mn is None else min(self.mn, mn)
         self.mx = mx if self.mx is None else max(self.mx, mx)
@@ -743,9 +811,7 @@ class Calibrator:
         n = t.numel()
         if n == 0:
             return
-        if self.out_cnt < NUM_SAMPLES:
-            take = min(NUM_SAMPLES - self.out_cnt, n)
-            self.head.append(t.reshape(-1)[:take].cpu().numpy())
+        self._take(t)
         if self._ws is None:
             self._ws = torch.zeros(int(L.i8ie_minmax_workspace_bytes()), dtype=torch.uint8, device=t.device)
             self._out = torch.empty(2, dtype=torch.float32, device=t.device)
@@ -760,12 +826,16 @@ class Calibrator:
         L = _lib.load()
         if self.out_cnt == 0:
             raise RuntimeError("convert() after prepare() needs at least one calibration forward pass")
-        if self.out_cnt <= NUM_SAMPLES:
+        cnt = min(self.out_cnt, NUM_SAMPLES)
+        if self.mode == "reference":
+            buf = np.sort(self.slots)                       # calibrator.cc:25
+            mn, mx = buf[0], buf[cnt - 1]                   # :26-27 with quantile 1
+        elif self.out_cnt <= NUM_SAMPLES:
             buf = np.zeros(NUM_SAMPLES, np.float32)        # value-initialised slots (layer.cc:33)
             head = np.concatenate(self.head)
             buf[:head.size] = head
             buf.sort()                                      # calibrator.cc:25
-            mn, mx = buf[0], buf[self.out_cnt - 1]          # :26-27 with quantile 1
+            mn, mx = buf[0], buf[cnt - 1]                   # :26-27 with quantile 1
         else:
             mn, mx = self.mn, self.mx
         sc, zp = C.c_float(), C.c_uint8()
@@ -1083,13 +1153,14 @@ class Conv2d(_BaseLayer):
             self._cal.sample_range(y, mm)
         return TensorF32(_Storage(y), [n, kc, oh, ow])
 
-    def _plan(self, n, c, h, w, cp, impl):
-        key = (n, c, h, w, cp, impl)
+    def _plan(self, n, c, h, w, cp, impl, out_cp=None):
+        kc, _, kh, kw = self._qw_shape
+        out_cp = out_cp or _act_pitch(kc)
+        key = (n, c, h, w, cp, impl, out_cp)
         p = self._plans.get(key)
         if p is None:
             L = _lib.load()
-            kc, _, kh, kw = self._qw_shape
-            p = L.i8ie_conv2d_plan_create(n, c, h, w, cp, kc, kh, kw, self._stride, self._pad, _act_pitch(kc),
+            p = L.i8ie_conv2d_plan_create(n, c, h, w, cp, kc, kh, kw, self._stride, self._pad, out_cp,
                                           self._packed_for(cp).data_ptr(), self._kc_pad, impl)
             if not p:
                 raise I8ieError(f"conv2d_plan_create failed: {_lib.last_error()}")
@@ -1120,8 +1191,9 @@ class Conv2d(_BaseLayer):
         ow = (w - kw + 2 * self._pad) // self._stride + 1
         return [n, kc, oh, ow], (n, kc, oh, ow, _act_pitch(kc))
 
-    def _forward_u8(self, x, acc_out=None, impl=0, relu=None):
+    def _forward_u8(self, x, acc_out=None, impl=0, relu=None, out_cp=None):
         # Conv2d::forward_prop(Tensor<u8>&&), conv2d.cc:100-142
+        # out_cp: channel pitch of the output (default _act_pitch(kc); a pool consumer may ask for round_up(kc, 16))
         L = _lib.load()
         (n, kc, oh, ow), _ = self._out_meta(x)
         _, c, h, w = x._shape
@@ -1131,10 +1203,10 @@ class Conv2d(_BaseLayer):
         if quant is not None:
             # the input is a not-yet-launched quantise of an fp32 image: a stem-eligible first
             # layer consumes the fp32 image directly (quantise fused into its operand staging)
-            y = self.forward_quantize_fused(quant.src, quant.scale, quant.zp, relu=relu)
+            y = self.forward_quantize_fused(quant.src, quant.scale, quant.zp, relu=relu, out_cp=out_cp)
             if y is not None:
                 return y
-        out_cp = _act_pitch(kc)
+        out_cp = out_cp or _act_pitch(kc)
         oc, _ = self._offsets(x._zp, x.scale(), True)
         # row mode (stride 1, channel count not a multiple of 128): physically padded input, K = (filter row,
         # contiguous kw * cp run) — AlexNet conv2 runs 20 K blocks instead of 25
@@ -1146,7 +1218,7 @@ class Conv2d(_BaseLayer):
         if cpx:
             xp = x._as_padded_nhwc(n, c, h, w, cpx, self._pad)
             out = _u8_empty(n * oh * ow * out_cp, xp.device)
-            plan = self._plan(n, c, h, w, cpx, 4)
+            plan = self._plan(n, c, h, w, cpx, 4, out_cp)
             self._last_impl = 4
             check(L.i8ie_conv2d_u8(plan, xp.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
                                    float(self._w_scale), float(self._scale), x._zp, self._zp, 1 if relu else 0,
@@ -1154,7 +1226,7 @@ class Conv2d(_BaseLayer):
             return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
         buf, cp = x._as_nhwc(n, c, h, w)
         out = _u8_empty(n * oh * ow * out_cp, buf.device)
-        plan = self._plan(n, c, h, w, cp, impl)
+        plan = self._plan(n, c, h, w, cp, impl, out_cp)
         self._last_impl = int(L.i8ie_conv2d_plan_impl(plan))   # 1 SIMT, 2 tcgen05 im2col, 3 tcgen05 stem
         flags = 1 if relu else 0
         check(L.i8ie_conv2d_u8(plan, buf.data_ptr(), out.data_ptr(), oc.data_ptr(), x.scale(),
@@ -1162,7 +1234,7 @@ class Conv2d(_BaseLayer):
                                acc_out.data_ptr() if acc_out is not None else None, _stream()), "conv2d_u8")
         return _new_u8_nhwc(out, n, kc, oh, ow, out_cp, self._scale, self._zp)
 
-    def forward_quantize_fused(self, x, in_scale, in_zp, acc_out=None, relu=None):
+    def forward_quantize_fused(self, x, in_scale, in_zp, acc_out=None, relu=None, out_cp=None):
         """Module.__call__'s input quantise (module.py:20) fused into this convolution
         (i8ie_conv2d_f32_u8). Only stem-eligible layers (C <= 4, stride 4/8) support it;
         returns None otherwise so the caller falls back to quantize() + __call__()."""
@@ -1173,14 +1245,14 @@ class Conv2d(_BaseLayer):
         kc, cw, kh, kw = self._qw_shape
         if c != cw or c > 4 or self._stride not in (4, 8):
             return None
-        plan = self._plan(n, c, h, w, _r16(c), 0)
+        out_cp = out_cp or _act_pitch(kc)
+        plan = self._plan(n, c, h, w, _r16(c), 0, out_cp)
         if int(L.i8ie_conv2d_plan_impl(plan)) != 3:
             return None
         in_scale = float(np.float32(in_scale))
         oh = (h - kh + 2 * self._pad) // self._stride + 1
         ow = (w - kw + 2 * self._pad) // self._stride + 1
         oc, _ = self._offsets(int(in_zp), in_scale, True)
-        out_cp = _act_pitch(kc)
         ptr, slot, dev = _src_ptrs(x)
         out = _u8_empty(n * oh * ow * out_cp, dev)
         flags = 1 if (self.fuse_relu if relu is None else relu) else 0

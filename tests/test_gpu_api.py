@@ -138,6 +138,31 @@ def test_calibrator_matches_reference_when_deterministic():
         assert np.float32(o.scale) == np.float32(es) and o.zero_point == int(ez), tag
 
 
+def test_calibrator_reference_mode_is_seeded_and_reference_like():
+    """Opt-in emulation of the reference's 1000-slot random-replacement sample (calibrator.cc:6-23): on a ramp the
+    range must come from the END of the stream (the reference's sample is ~1000 of the last few thousand values),
+    reproducibly for a fixed seed; the default mode keeps the true min/max."""
+    from int8inferenceengine_b200 import backend as B
+    n = 200000
+    ramp = torch.arange(n, dtype=torch.float32, device="cuda")
+    res = []
+    for rep in range(2):
+        B.Calibrator.seed, B.Calibrator._instances = 7, 0
+        c = B.Calibrator(mode="reference")
+        c.sample(ramp[:120000])
+        c.sample(ramp[120000:])
+        lo, hi = float(np.sort(c.slots)[0]), float(np.sort(c.slots)[-1])
+        res.append((lo, hi, c.get_range()))
+        assert hi > n - 40 and n - 40000 < lo < n - 6000      # min of 1000 geometric(1/2001) look-backs ~ 14 k
+    assert res[0] == res[1]
+    d = B.Calibrator()                                        # default: deterministic true min / max
+    d.sample(ramp)
+    assert (d.mn, d.mx) == (0.0, float(n - 1))
+    s_ref, _ = res[0][2]
+    s_mm, _ = d.get_range()
+    assert np.isclose(s_ref, s_mm, rtol=1e-3)                 # max within a few values of the end, min clamped to 0 (calibrator.cc:28)
+
+
 def test_error_paths():
     L = i8ie.Linear(4, 4)
     L.convert()
