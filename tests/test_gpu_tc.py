@@ -119,6 +119,25 @@ def _run_conv_parity(geom, impl=2):
     assert np.array_equal(out_r.numpy(), port.relu_u8(exp, out_zp))
 
 
+SMALL_M = [  # AlexNet conv2..conv5 at batch 1 .. 16 (BASELINE config 5's small end): one to a dozen pair tiles
+    (1, 256, 13, 13, 384, 3, 1, 1), (1, 384, 13, 13, 384, 3, 1, 1), (4, 384, 13, 13, 256, 3, 1, 1),
+    (16, 384, 13, 13, 256, 3, 1, 1), (8, 256, 13, 13, 384, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("geom", SMALL_M)
+def test_tc_conv_small_m(geom):
+    """Small-M convolutions (a handful of tiles, most of the chip idle): accumulators, bytes, pad lanes and relu
+    against the oracle."""
+    _run_conv_parity(geom)
+
+
+@pytest.mark.parametrize("geom", [(1, 96, 27, 27, 256, 5, 1, 2), (3, 96, 27, 27, 256, 5, 1, 2)])
+def test_tc_conv_small_m_row_mode(geom):
+    """The same for a row-mode plan (AlexNet conv2 at batch 1 / 3: physically padded input, no border table)."""
+    _run_conv_parity(geom, impl=4)
+
+
 @pytest.mark.parametrize("geom", PAIR)
 def test_tc_conv_cta_pair(geom):
     """tcgen05.mma.cta_group::2 kernel (two SMs per 256-row tile)."""
