@@ -686,9 +686,12 @@ def run_ours(args):
             "data": "synthetic",
             "config": workload_config(topo, gbatch, world),
             "run": {"per_gpu_batch": lbatch, "ring_batches": ring, "ring_mb": round(ring * bytes_per_batch / 1e6),
-                    "step": ("forward + result exchange captured as ONE CUDA graph per ring buffer (one host enqueue per "
-                             f"step); exchange = {type(exchange).__name__}: pack kernel pushes [agreement count | logits] "
-                             "into every rank's buffer with NVLink peer stores, unpack kernel waits for all ranks' step flags"
+                    "step": (("forward + result exchange captured as ONE CUDA graph per ring buffer (one host enqueue per "
+                              "step); exchange = PeerExchange: pack kernel pushes [agreement count | logits] into every "
+                              "rank's buffer with NVLink peer stores, unpack kernel waits for all ranks' step flags"
+                              if type(exchange).__name__ == "PeerExchange" else
+                              "forward captured as a CUDA graph per ring buffer, then ResultExchange: pack kernel, one NCCL "
+                              "all-gather, unpack kernel (the peer-memory exchange could not be set up on this box)")
                              if world > 1 else "i8ie.Module.__call__ on a device-resident batch (CUDA-graph replay)"),
                     "collectives": "none on the data path; result exchange only" if world > 1 else "none",
                     "scaling_note": "N=1 runs BASELINE config 3 (batch 100), N>1 config 4 (batch 1000 sharded): compare "

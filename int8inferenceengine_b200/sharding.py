@@ -158,26 +158,52 @@ class PeerExchange:
             cap += 1
         self.chunk = int(self._L.i8ie_top1_chunk_bytes(cap, cols))
         nbytes = int(self._L.i8ie_peer_exchange_bytes(self.world, self.chunk))
+        # Every step below that can fail on ONE rank (allocation, IPC export, mapping a peer) is followed by an
+        # exchange of the outcome, so that all ranks raise together instead of some of them waiting in a collective.
         mine = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        with torch.cuda.device(self.device):
-            self._check(self._L.i8ie_peer_alloc(nbytes, C.byref(mine), handle), "peer_alloc")
-        self._mine = mine.value
-        handles = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(handles, bytes(handle))
-        self._opened = []
-        bases = (C.c_void_p * self.world)()
-        for p in range(self.world):
-            if p == self.rank:
-                bases[p] = self._mine
-                continue
-            ptr = C.c_void_p()
-            buf = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+        err = None
+        try:
             with torch.cuda.device(self.device):
-                self._check(self._L.i8ie_peer_open(buf, C.byref(ptr)), f"peer_open(rank {p})")
-            bases[p] = ptr.value
-            self._opened.append(ptr.value)
+                self._check(self._L.i8ie_peer_alloc(nbytes, C.byref(mine), handle), "peer_alloc")
+        except Exception as e:  # noqa: BLE001
+            err = str(e)
+        self._mine = mine.value
+        handles = [(err, bytes(handle))]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (err, bytes(handle)))
+        self._opened = []
+        bad = [f"rank {r}: {h[0]}" for r, h in enumerate(handles) if h[0] is not None]
+        bases = (C.c_void_p * self.world)()
+        if not bad:
+            try:
+                for p in range(self.world):
+                    if p == self.rank:
+                        bases[p] = self._mine
+                        continue
+                    ptr = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[p][1])
+                    with torch.cuda.device(self.device):
+                        self._check(self._L.i8ie_peer_open(buf, C.byref(ptr)), f"peer_open(rank {p})")
+                    bases[p] = ptr.value
+                    self._opened.append(ptr.value)
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+            if self.world > 1:
+                outcomes = [None] * self.world
+                dist.all_gather_object(outcomes, err)
+                bad = [f"rank {r}: {o}" for r, o in enumerate(outcomes) if o is not None]
+            elif err is not None:
+                bad = [err]
+        if bad:
+            with torch.cuda.device(self.device):
+                for ptr in self._opened:
+                    self._L.i8ie_peer_close(ptr)
+                if self._mine:
+                    self._L.i8ie_peer_free(self._mine)
+            self._opened, self._mine = [], None
+            raise RuntimeError("peer-memory exchange unavailable (" + "; ".join(bad) + ")")
         self._bases = bases
         self.seq = torch.zeros(2, dtype=torch.int64, device=self.device)    # [0] = step counter
         self.logits_all = torch.empty(self.global_batch, cols, dtype=torch.float32, device=self.device)
@@ -226,11 +252,17 @@ class PeerExchange:
 
 def make_exchange(global_batch: int, cols: int, device, kind: str | None = None):
     """Result exchange for the sharded step: 'peer' (NVLink peer memory, default on GPUs) or 'nccl'
-    (ResultExchange). I8IE_EXCHANGE overrides."""
+    (ResultExchange). I8IE_EXCHANGE overrides. If the peer buffers cannot be set up (no CUDA IPC in the
+    container, no peer access), every rank learns it together and all of them fall back to the NCCL exchange."""
     import os
+    import warnings
     kind = kind or os.environ.get("I8IE_EXCHANGE", "peer")
     if kind == "peer":
-        return PeerExchange(global_batch, cols, device)
+        try:
+            return PeerExchange(global_batch, cols, device)
+        except RuntimeError as e:
+            warnings.warn(f"i8ie: {e}; using the NCCL result exchange")
+            return ResultExchange(global_batch, cols, device)
     if kind == "nccl":
         return ResultExchange(global_batch, cols, device)
     raise ValueError(f"unknown exchange kind {kind!r}")
