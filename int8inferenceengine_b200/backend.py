@@ -1267,7 +1267,7 @@ class Conv2d(_BaseLayer):
 
 # ---- CUDA-graph replay of a whole quantised forward (used by api.Module.__call__) ------------
 
-MAX_DIRECT_GRAPHS = int(os.environ.get("I8IE_DIRECT_GRAPHS", "8"))   # graphs with the input address baked in, per (shape, device, epoch)
+MAX_DIRECT_GRAPHS = int(os.environ.get("I8IE_DIRECT_GRAPHS", "16"))   # graphs with the input address baked in, per (shape, device, epoch)
 
 
 class _GraphOutStorage:
