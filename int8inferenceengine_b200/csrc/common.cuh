@@ -96,9 +96,10 @@ inline void launch_cluster_pdl(int cluster_x, void (*kernel)(KArgs...), dim3 gri
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  // cluster_x = -1: an EXPLICIT cluster of one CTA (kernels that use shared::cluster bulk copies within their own CTA)
   at[1].id = cudaLaunchAttributeClusterDimension;
-  at[1].val.clusterDim.x = (unsigned)cluster_x; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = cluster_x > 1 ? 2 : 1;
+  at[1].val.clusterDim.x = (unsigned)(cluster_x < 0 ? 1 : cluster_x); at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = (cluster_x > 1 || cluster_x < 0) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through check_launch()
 }
 

@@ -1295,7 +1295,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
     StemCursor ccur, fcur;
     ccur.init(t_begin, sp.pairs);
     fcur.s = 0; fcur.ph = 0;
-    uint32_t sprev_slot = 0;
+    uint32_t sprev_slot = 0, sprev_ph = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++it, ccur.next_tile(sp.pairs)) {
       const int p0 = ccur.pr * 2;
       const uint32_t s = ccur.s, ph = ccur.ph;
@@ -1318,15 +1318,26 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
       const uint32_t st = sA_u + s * (uint32_t)a_stage;
       const uint32_t sf = sF_u + fs * (uint32_t)sp.f_stage_bytes;
       int i_start = 0;
+      // The previous tile's `full` phase is complete — i.e. ITS bulk copy (below) has finished reading the stage this
+      // tile is about to overwrite — before any row of this tile is written.
+      if (it != 0 && !dead && !ptx::mbar_wait(&ctl->full[sprev_slot], sprev_ph)) { tc_fail(6); dead = true; }
       if (!first) {
-        // tile row i is row i + 8 of the previous tile: same region (i & 3), two 1 KB slots further on
+        // Tile row i is row i + 8 of the previous tile: same region (i & 3), two 1 KB slots further on. The carried
+        // rows of a region are contiguous in both stages, so ONE thread hands them to the bulk-copy engine (shared ->
+        // shared, completing on this stage's `full` barrier next to the converters' arrivals) instead of every warp
+        // moving a row through registers: those lds / sts stalled for ~1500 clk per tile behind the operand reads of
+        // the previous tile's MMAs, on the converters' critical path.
         const uint32_t sprev = sA_u + sprev_slot * (uint32_t)a_stage;
-        for (int i = pw; i < i_new; i += kProdW) {
-          const uint32_t off = (uint32_t)((i & 3) * sp.nsl + (i >> 2)) * 1024u;
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-            if (sx_ok[u]) ptx::sts128(st + off + (uint32_t)(lane + 32 * u) * 16u,
-                                      ptx::lds128(sprev + off + 2048u + (uint32_t)(lane + 32 * u) * 16u));
+        if (pw == 0 && lane == 0 && !dead) {
+          uint32_t bytes = 0;
+          for (int r = 0; r < 4 && r < i_new; ++r) bytes += (uint32_t)((i_new - r + 3) >> 2) * 1024u;
+          ptx::mbar_expect_tx(&ctl->full[s], bytes);
+          const uint32_t bar = ptx::smem_u32(&ctl->full[s]);
+          for (int r = 0; r < 4 && r < i_new; ++r) {
+            const uint32_t cnt = (uint32_t)((i_new - r + 3) >> 2);      // carried rows r, r + 4, ... < i_new
+            ptx::bulk_copy_to_cluster(st + (uint32_t)(r * sp.nsl) * 1024u, sprev + (uint32_t)(r * sp.nsl + 2) * 1024u,
+                                      cnt * 1024u, bar);
+          }
         }
         i_start = i_new;
       }
@@ -1395,7 +1406,7 @@ __global__ void __launch_bounds__((stem_threads<BN, FQ>()), 1) tc_stem2_kernel(c
         ptx::mbar_arrive(&f_empty[fs]);
       }
       if (pw == 0 && lane == 0) stem_trace(sp, it, 6);
-      sprev_slot = s;
+      sprev_slot = s; sprev_ph = ph;
     }
   } else {
     const int quad = warp & 3;
@@ -2275,7 +2286,7 @@ int launch_stem2_bn(const GemmGeom& g, const StemGeom& s, const uint8_t* xs, con
   const int grid = tiles < num_sms() ? tiles : num_sms();
   const int threads = fq ? stem_threads<BN, true>() : stem_threads<BN, false>();
   PdlFamily fam_(kPdlStem);
-  launch_pdl(kern, dim3(grid), dim3(threads), (size_t)smem, stream, tmB, p, sp);
+  launch_cluster_pdl(fq ? -1 : 1, kern, dim3(grid), dim3(threads), (size_t)smem, stream, tmB, p, sp);
   if (trace_path != nullptr) {
     std::vector<long long> h(kTraceTiles * kTraceEvents);
     I8IE_CUDA_OK(cudaDeviceSynchronize());

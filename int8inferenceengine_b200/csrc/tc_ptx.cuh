@@ -339,6 +339,10 @@ __device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster, uint3
                ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
                : "memory");
 }
+// adds bytes to the current phase's pending transaction count without arriving
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void st_cluster128(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
