@@ -122,11 +122,12 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
-// L2 prefetch (no shared-memory destination, nothing to wait for). A TMA / bulk load that MISSES L2 is
-// tracked by the SM until DRAM answers, and the SM only tracks ~14 KB of such requests: measured on B200,
-// a DRAM-sourced bulk stream delivers ~8 B/clk/SM (2.3 TB/s over the chip) against 46.6 B/clk/SM from L2.
-// Streams that come from DRAM (the fp32 network input, fc weights) are therefore prefetched into L2 a few
-// tiles ahead with these fire-and-forget requests and then loaded from L2.
+// L2 prefetch (no shared-memory destination, nothing to wait for). Measured on B200 (tools/ubench/i8_peak.cu,
+// dram_bulk, profiles/r02_stem_probes.md): what a DRAM-sourced bulk stream delivers depends on the CHUNK size —
+// contiguous 16 KB copies reach 6.0 TB/s chip-wide with three in flight per SM, 7 KB copies 3.6 - 4.0 TB/s, and
+// 128-byte rows that lie kilobytes apart (a tiled box of a row-major weight matrix) 2.3 TB/s — and a prefetch ahead
+// of large contiguous copies costs 15 %. The stem kernel, whose per-plane runs are ~7 KB, keeps its prefetch
+// (I8IE_STEM2_PF); the fc weight stream uses contiguous pre-swizzled 16 KB blocks instead (TcParams::w_tiled).
 __device__ __forceinline__ void prefetch_l2_bulk(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
