@@ -405,6 +405,14 @@ int i8ie_fc_weight_tiled_attach(const int8_t* w, int n_pad, int ldw, int8_t* w_t
   I8IE_REQUIRE(w && w_tiled && i8ie_fc_weight_tiled_bytes(n_pad, ldw) > 0, "fc_weight_tiled_attach: bad arguments");
   int rc = tc_fc_tile_weights(w, n_pad, ldw, w_tiled, (cudaStream_t)stream);
   if (rc != I8IE_OK) return rc;
+  // The fc kernels request their first weight stages BEFORE griddepcontrol.wait (the weights do not depend on the
+  // previous kernel of a forward) — so the copy must be complete, not merely ordered on the stream, before the pair
+  // is registered. Once per model, never inside a capture.
+  cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing((cudaStream_t)stream, &cst) == cudaSuccess && cst == cudaStreamCaptureStatusNone)
+    I8IE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  else
+    return I8IE_OK;   // capturing: leave the pair unregistered (the K-major weights are used)
   std::lock_guard<std::mutex> lk(g_tiled_mu);
   for (auto& e : g_tiled)
     if (e.w == w) { e = TiledWeight{w, w_tiled, n_pad, ldw}; return I8IE_OK; }
